@@ -1,0 +1,383 @@
+// adapt.cuh -- adaptive block RLE (reference: src/transform.cpp:25-134, 162-216, 294-361;
+// header src/headers.cpp:18-105).
+//
+// ENCODE = three kernels per batch:
+//   adapt_cost_kernel   for every candidate block size B = 8 << k (k = 0..7, B <= W, B <= H) and
+//                       every block: the MNP-5 size of the block read row-major (horizontal)
+//                       and column-major (vertical); keeps min and the direction bit
+//                       (tie -> horizontal, src/transform.cpp:114).  A group of L lanes owns a
+//                       block: each lane folds a contiguous chunk of the block's sequence into
+//                       a RunSum (runsum.cuh), the group reduces them with warp shuffles.
+//   adapt_select_kernel per file: total(B) = 24 + ceil(nb/8) + sum of block sizes; smallest
+//                       total wins, ties keep the smaller B (strict '<', :319); writes the
+//                       header <W><H><B> big endian + direction bits (32 blocks per warp
+//                       ballot, block 0 = MSB) and the exclusive scan of the block sizes.
+//   adapt_emit_kernel   RLE-encodes every block of the winning size in its direction at its
+//                       scanned offset (same lane-chunk decomposition, RunSum prefix per lane).
+// DECODE: block boundaries depend on the decoded data itself (fresh RLE state per block,
+// a block ends when bw*bh bytes exist), so v1 walks each file's token stream with one thread.
+#pragma once
+#include "runsum.cuh"
+#include "scan.cuh"
+
+namespace hcd {
+
+constexpr int AD_NCAND = 8;                 // INIT_RLE_BLOCK_SIZE 8, MAX_RLE_DOUBLING_STEPS 7
+constexpr u32 AD_CHUNK = 16;                // target elements per lane
+
+struct BlockGeom { u64 base; u32 bw, bh; };
+
+HC_HD u64 ad_nblocks(u64 w, u64 h, u64 b) { return ((w + b - 1) / b) * ((h + b - 1) / b); }
+
+HC_HD BlockGeom ad_geom(u64 w, u64 h, u64 b, u64 idx)
+{
+    u64 bil = (w + b - 1) / b;
+    u64 bx = (idx % bil) * b, by = (idx / bil) * b;
+    BlockGeom g;
+    g.base = by * w + bx;
+    g.bw = (u32)(bx + b > w ? w - bx : b);
+    g.bh = (u32)(by + b > h ? h - by : b);
+    return g;
+}
+
+// candidate k is evaluated iff k == 0 or (8<<k) <= min(w, h)   (src/transform.cpp:309-315)
+HC_HD bool ad_cand_valid(u64 w, u64 h, int k) { u64 b = 8ull << k; return k == 0 || (b <= w && b <= h); }
+
+// offset (in u32 entries) of candidate k's per-block table inside a file's cost scratch
+HC_HD u64 ad_kbase(u64 w, u64 h, int k)
+{
+    u64 o = 0;
+    for (int i = 0; i < k; i++)
+        if (ad_cand_valid(w, h, i)) o += ad_nblocks(w, h, 8ull << i);
+    return o;
+}
+
+// lanes per block for block size b: power of two, ~AD_CHUNK elements per lane, <= 32
+HC_HD u32 ad_lanes(u64 b)
+{
+    u64 n = b * b;
+    u32 l = 1;
+    while (l < 32 && (u64)l * AD_CHUNK < n) l <<= 1;
+    return l;
+}
+
+// sequential reader of a block in horizontal (row-major) or vertical (column-major) order
+struct BlockCursor {
+    const u8 *p;       // matrix + block base
+    u64 w;             // matrix width
+    u32 inner, i, o;   // inner extent (bw for hor, bh for ver), inner index, outer index
+    bool hor;
+};
+
+HC_DEV void bc_seek(BlockCursor &c, const u8 *mat, u64 w, const BlockGeom &g, bool hor, u32 pos)
+{
+    c.p = mat + g.base;
+    c.w = w;
+    c.hor = hor;
+    c.inner = hor ? g.bw : g.bh;
+    c.o = pos / c.inner;
+    c.i = pos % c.inner;
+}
+
+HC_DEV u32 bc_next(BlockCursor &c)
+{
+    u64 a = c.hor ? (u64)c.o * c.w + c.i : (u64)c.i * c.w + c.o;
+    u32 b = ldg8(c.p + a);
+    if (++c.i == c.inner) { c.i = 0; c.o++; }
+    return b;
+}
+
+HC_DEV RunSum rs_shfl_down(const RunSum &s, unsigned d)
+{
+    RunSum r;
+    r.head = shfl_down(s.head, d); r.tail = shfl_down(s.tail, d);
+    r.inner = shfl_down(s.inner, d); r.meta = shfl_down(s.meta, d);
+    return r;
+}
+HC_DEV RunSum rs_shfl_up(const RunSum &s, unsigned d)
+{
+    RunSum r;
+    r.head = shfl_up(s.head, d); r.tail = shfl_up(s.tail, d);
+    r.inner = shfl_up(s.inner, d); r.meta = shfl_up(s.meta, d);
+    return r;
+}
+
+// RunSum of elements [lo, hi) of a block sequence
+HC_DEV RunSum ad_chunk_sum(const u8 *mat, u64 w, const BlockGeom &g, bool hor, u32 lo, u32 hi)
+{
+    RunSum s = rs_empty();
+    if (lo < hi) {
+        BlockCursor c;
+        bc_seek(c, mat, w, g, hor, lo);
+        for (u32 i = lo; i < hi; i++) rs_push(s, bc_next(c));
+    }
+    return s;
+}
+
+// ordered reduction over the L lanes of a group; result valid in group lane 0
+HC_DEV RunSum ad_group_reduce(RunSum s, u32 L, u32 gl)
+{
+    for (u32 d = 1; d < L; d <<= 1) {
+        RunSum o = rs_shfl_down(s, d);
+        if ((gl & (2 * d - 1)) == 0 && gl + d < L) s = rs_combine(s, o);
+    }
+    return s;
+}
+
+constexpr int AD_COST_TPB = 256;
+
+HC_KERNEL HC_LAUNCH_BOUNDS(AD_COST_TPB, 4)
+adapt_cost_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT width,
+                  const u64 *HC_RESTRICT height, u32 nf, u32 *HC_RESTRICT cost, u64 cost_stride, u32 nchunks)
+{
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const int k = (int)(blockIdx.x % AD_NCAND);
+    const u32 chunk_id = blockIdx.x / AD_NCAND;
+    const u64 b = 8ull << k;
+    const u32 L = ad_lanes(b), G = 32u / L, gl = lane % L, gi = lane / L;
+    for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
+        const u64 w = width[f], h = height[f];
+        if (w < 8 || h < 8 || !ad_cand_valid(w, h, k)) continue;
+        const u8 *mat = in + in_off[f];
+        u32 *tab = cost + (u64)f * cost_stride + ad_kbase(w, h, k);
+        const u64 nb = ad_nblocks(w, h, b);
+        const u64 ngroups = (nb + G - 1) / G;
+        const u64 stride = (u64)nchunks * (AD_COST_TPB / 32);
+        for (u64 grp = (u64)chunk_id * (AD_COST_TPB / 32) + wid; grp < ngroups; grp += stride) {
+            const u64 blk = grp * G + gi;
+            const bool live = blk < nb;
+            BlockGeom g = ad_geom(w, h, b, live ? blk : 0);
+            const u32 n = live ? g.bw * g.bh : 0u;
+            const u32 per = (n + L - 1) / L;
+            u32 lo = gl * per, hi = lo + per;
+            if (lo > n) lo = n;
+            if (hi > n) hi = n;
+            RunSum sh = ad_group_reduce(ad_chunk_sum(mat, w, g, true, lo, hi), L, gl);
+            RunSum sv = ad_group_reduce(ad_chunk_sum(mat, w, g, false, lo, hi), L, gl);
+            if (live && gl == 0) {
+                u32 ch = rs_cost_final(sh), cv = rs_cost_final(sv);
+                tab[blk] = ch <= cv ? (ch | 0x80000000u) : cv;   // bit 31 = horizontal
+            }
+        }
+    }
+}
+
+// one CTA per file
+HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
+adapt_select_kernel(const u64 *HC_RESTRICT width, const u64 *HC_RESTRICT height, u32 nf,
+                    const u32 *HC_RESTRICT cost, u64 cost_stride, u32 *HC_RESTRICT blk_off, u64 off_stride,
+                    u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u64 *HC_RESTRICT out_len,
+                    u64 *HC_RESTRICT chosen_b, i32 *HC_RESTRICT status)
+{
+    HC_SHARED u64 red[NW];
+    HC_SHARED u64 s_total[AD_NCAND];
+    HC_SHARED u32 s_wsum[NW];
+    HC_SHARED int s_best;
+    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
+        const u64 w = width[f], h = height[f];
+        if (w < 8 || h < 8) {                              // src/transform.cpp:300-304
+            if (tid == 0) { out_len[f] = 0; if (chosen_b) chosen_b[f] = 0; status[f] = 12; }
+            continue;
+        }
+        const u32 *ctab = cost + (u64)f * cost_stride;
+        for (int k = 0; k < AD_NCAND; k++) {
+            if (!ad_cand_valid(w, h, k)) { if (tid == 0) s_total[k] = ~0ull; continue; }
+            const u64 nb = ad_nblocks(w, h, 8ull << k);
+            const u32 *t = ctab + ad_kbase(w, h, k);
+            u64 acc = 0;
+            for (u64 i = tid; i < nb; i += 256) acc += t[i] & 0x7fffffffu;
+            for (int d = 16; d > 0; d >>= 1) acc += shfl_xor64(acc, d);
+            if (lane == 0) red[wid] = acc;
+            syncthreads();
+            if (tid == 0) {
+                u64 tot = 24 + (nb + 7) / 8;               // header + direction bytes
+                for (int i = 0; i < NW; i++) tot += red[i];
+                s_total[k] = tot;
+            }
+            syncthreads();
+        }
+        if (tid == 0) {
+            int best = 0;
+            for (int k = 1; k < AD_NCAND; k++)
+                if (s_total[k] != ~0ull && s_total[k] < s_total[best]) best = k;   // strict: ties keep smaller B
+            s_best = best;
+            out_len[f] = s_total[best];
+            if (chosen_b) chosen_b[f] = 8ull << best;
+            status[f] = 0;
+        }
+        syncthreads();
+        const int kb = s_best;
+        const u64 b = 8ull << kb;
+        const u64 nb = ad_nblocks(w, h, b);
+        const u32 *t = ctab + ad_kbase(w, h, kb);
+        u8 *o = out + out_off[f];
+        // header, big endian (src/headers.cpp:27-37)
+        if (tid < 24) {
+            u64 v = tid < 8 ? w : (tid < 16 ? h : b);
+            o[tid] = (u8)(v >> (8 * (7 - (tid & 7))));
+        }
+        // direction bits: block 0 = MSB of the first byte, zero padded (src/headers.cpp:43-60)
+        const u64 dir_bytes = (nb + 7) / 8;
+        for (u64 i0 = (u64)wid * 32; i0 < nb; i0 += 256) {
+            u64 i = i0 + lane;
+            u32 m = ballot(i < nb && (t[i < nb ? i : 0] >> 31));
+            u32 rev = brev(m);
+            if (lane < 4) {
+                u64 bi = i0 / 8 + lane;
+                if (bi < dir_bytes) o[24 + bi] = (u8)(rev >> (24 - 8 * lane));
+            }
+        }
+        // exclusive scan of the block sizes -> offset of each block's RLE stream (after header)
+        u32 *bo = blk_off + (u64)f * off_stride;
+        u32 carry = 0;
+        for (u64 i0 = 0; i0 < nb; i0 += 256) {
+            u64 i = i0 + tid;
+            u32 v = i < nb ? (t[i] & 0x7fffffffu) : 0u;
+            u32 inc = v;
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 x = shfl_up(inc, d);
+                if (lane >= (u32)d) inc += x;
+            }
+            if (lane == 31) s_wsum[wid] = inc;
+            syncthreads();
+            u32 wbase = 0, tot = 0;
+            for (u32 j = 0; j < NW; j++) { if (j < wid) wbase += s_wsum[j]; tot += s_wsum[j]; }
+            if (i < nb) bo[i] = carry + wbase + inc - v;
+            carry += tot;
+            syncthreads();
+        }
+    }
+}
+
+constexpr int AD_EMIT_TPB = 256;
+
+HC_KERNEL HC_LAUNCH_BOUNDS(AD_EMIT_TPB, 4)
+adapt_emit_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT width,
+                  const u64 *HC_RESTRICT height, u32 nf, const u32 *HC_RESTRICT cost, u64 cost_stride,
+                  const u32 *HC_RESTRICT blk_off, u64 off_stride, const u64 *HC_RESTRICT chosen_b,
+                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status)
+{
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
+        if (status[f] != 0) continue;
+        const u64 w = width[f], h = height[f], b = chosen_b[f];
+        int k = 0;
+        while ((8ull << k) < b) k++;
+        const u32 L = ad_lanes(b), G = 32u / L, gl = lane % L, gi = lane / L;
+        const u8 *mat = in + in_off[f];
+        const u32 *tab = cost + (u64)f * cost_stride + ad_kbase(w, h, k);
+        const u32 *bo = blk_off + (u64)f * off_stride;
+        const u64 nb = ad_nblocks(w, h, b);
+        u8 *data = out + out_off[f] + 24 + (nb + 7) / 8;
+        const u64 ngroups = (nb + G - 1) / G;
+        const u64 stride = (u64)gridDim.x * (AD_EMIT_TPB / 32);
+        for (u64 grp = (u64)blockIdx.x * (AD_EMIT_TPB / 32) + wid; grp < ngroups; grp += stride) {
+            const u64 blk = grp * G + gi;
+            const bool live = blk < nb;
+            BlockGeom g = ad_geom(w, h, b, live ? blk : 0);
+            const u32 n = live ? g.bw * g.bh : 0u;
+            const bool hor = live ? (tab[blk] >> 31) : true;
+            const u32 per = (n + L - 1) / L;
+            u32 lo = gl * per, hi = lo + per;
+            if (lo > n) lo = n;
+            if (hi > n) hi = n;
+            // inclusive scan of the lane chunks' RunSums inside the group, then shift
+            RunSum inc = ad_chunk_sum(mat, w, g, hor, lo, hi);
+            for (u32 d = 1; d < L; d <<= 1) {
+                RunSum o = rs_shfl_up(inc, d);
+                if (gl >= d) inc = rs_combine(o, inc);
+            }
+            RunSum pre = rs_shfl_up(inc, 1);
+            if (gl == 0) pre = rs_empty();
+            if (lo < hi) {
+                BlockCursor c;
+                bc_seek(c, mat, w, g, hor, lo);
+                u32 curb = bc_next(c);
+                // run index of the first element of this chunk and bytes emitted before it
+                const bool is_final0 = (lo == n - 1);
+                const bool cont = rs_nonempty(pre) && rs_last(pre) == curb && !is_final0;
+                u32 kidx = cont ? pre.tail : 0u;
+                u8 *op = data + bo[blk] + rs_emitted_prefix(pre, !cont);
+                u32 q = kidx % 258u;
+                for (u32 i = lo; i < hi; i++) {
+                    // look one element ahead (may belong to the next lane's chunk)
+                    u32 nextb = 0x100u;
+                    if (i + 1 < n) nextb = bc_next(c);
+                    const bool next_cont = (nextb == curb) && (i + 1 != n - 1);
+                    if (q < 3u) *op++ = (u8)curb;
+                    if (q == 257u) *op++ = 255;
+                    else if (!next_cont && q >= 2u && i != n - 1) *op++ = (u8)(q - 2u);
+                    q = next_cont ? (q == 257u ? 0u : q + 1u) : 0u;
+                    curb = nextb;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// decode: one thread per file walks the token stream (block starts are data dependent)
+// ------------------------------------------------------------------------------------------
+HC_KERNEL HC_LAUNCH_BOUNDS(32, 1)
+adapt_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
+                    u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
+                    u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
+{
+    const u32 f = blockIdx.x;
+    if (f >= nf || threadIdx.x != 0) return;
+    const u64 m = in_len[f];
+    const u8 *src = in + in_off[f];
+    out_len[f] = 0;
+    if (m < 24) { status[f] = 10; return; }               // src/headers.cpp:67-71
+    u64 w = 0, h = 0, b = 0;
+    for (int i = 0; i < 8; i++) w = (w << 8) | src[i];
+    for (int i = 0; i < 8; i++) h = (h << 8) | src[8 + i];
+    for (int i = 0; i < 8; i++) b = (b << 8) | src[16 + i];
+    if (b == 0) { status[f] = 10; return; }               // reference: division by zero (UB)
+    const u64 nbx = w / b + (w % b != 0), nby = h / b + (h % b != 0);
+    // direction bytes are read lazily by the reference; missing ones -> 11 (src/headers.cpp:94-98)
+    const u64 avail_bits = (m - 24) * 8;
+    if ((nbx != 0 && nby != 0) && (nbx > avail_bits || nby > avail_bits || nbx * nby > avail_bits)) {
+        status[f] = 11;
+        return;
+    }
+    const u64 nb = nbx * nby;
+    const u64 dir_bytes = (nb + 7) / 8;
+    // w*h cannot overflow here: nb <= 8m blocks of at most b*b... guard explicitly anyway
+    if (h != 0 && w > ~0ull / h) { status[f] = 100; return; }
+    const u64 total = w * h;
+    out_len[f] = total;
+    if (!out) { status[f] = 0; return; }
+    if (total > out_cap[f]) { status[f] = 100; return; }
+    u8 *mat = out + out_off[f];
+    u64 pos = 24 + dir_bytes;
+    for (u64 i = 0; i < nb; i++) {
+        const bool hor = (src[24 + (i >> 3)] >> (7 - (i & 7))) & 1u;
+        BlockGeom g = ad_geom(w, h, b, i);
+        const u32 req = g.bw * g.bh, inner = hor ? g.bw : g.bh;
+        u8 *bp = mat + g.base;
+        u32 produced = 0, ci = 0, co = 0;
+        u32 match_byte = 0, match_count = 0;               // fresh state per block (:166-167)
+        while (produced < req) {
+            if (pos >= m) { status[f] = 14; return; }      // src/transform.cpp:170-174
+            u32 cur = src[pos++];
+            u32 len, val;
+            if (match_count == 3) { len = cur; val = match_byte; match_count = 0; }
+            else {
+                len = 1; val = cur;
+                if (match_byte == cur) match_count++; else { match_byte = cur; match_count = 1; }
+            }
+            if (produced + len > req) { status[f] = 13; return; }   // src/transform.cpp:180-184
+            for (u32 j = 0; j < len; j++) {
+                u64 a = hor ? (u64)co * w + ci : (u64)ci * w + co;
+                bp[a] = (u8)val;
+                if (++ci == inner) { ci = 0; co++; }
+            }
+            produced += len;
+        }
+    }
+    status[f] = pos != m ? 15 : 0;                         // src/transform.cpp:354-358
+}
+
+}  // namespace hcd

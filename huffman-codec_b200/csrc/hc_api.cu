@@ -1,0 +1,817 @@
+// hc_api.cu -- C ABI of libhc_b200.so (see include/hc_b200.h): stage launchers, the batched
+// host pipeline (huffCompress / huffDecompress of src/main.cpp:39-128) and small utility kernels.
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a -> libhc_b200.so.  There is no CPU
+// implementation behind these entry points.  (-DHC_EMU builds the SIMT-emulated test double used
+// by tests/emu only; see hc_emu.h.)
+#include "../../include/hc_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#ifdef HC_EMU
+#include "hc_emu.h"
+#include "hc_emu_cuda.h"
+#endif
+#include "hc_common.cuh"
+#include "scan.cuh"
+#include "diff.cuh"
+#include "rle.cuh"
+#include "adapt.cuh"
+#include "fgk.cuh"
+
+static std::atomic<uint64_t> g_launches{0};
+void hc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define HC_CUDA(x)                                         \
+    do {                                                   \
+        cudaError_t e_ = (x);                              \
+        if (e_ != cudaSuccess) return -(int)e_;            \
+    } while (0)
+#define HC_CHECK_LAUNCH() HC_CUDA(cudaGetLastError())
+
+namespace hcd {
+
+// ---------------------------------------------------------------- utility kernels
+HC_KERNEL offsets_scan_kernel(const u64 *HC_RESTRICT len, u64 *HC_RESTRICT off, u64 *HC_RESTRICT total,
+                              u32 nf, u32 align)
+{
+    HC_SHARED u64 wsum[NW];
+    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    u64 carry = 0;
+    for (u32 i0 = 0; i0 < nf; i0 += TPB) {
+        u32 i = i0 + tid;
+        u64 v = i < nf ? (len[i] + align - 1) / align * align : 0;
+        u64 inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 x = shfl_up64(inc, d);
+            if (lane >= (u32)d) inc += x;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        syncthreads();
+        u64 wbase = 0, tot = 0;
+        for (u32 j = 0; j < (u32)NW; j++) { if (j < wid) wbase += wsum[j]; tot += wsum[j]; }
+        if (i < nf) off[i] = carry + wbase + inc - v;
+        carry += tot;
+        syncthreads();
+    }
+    if (tid == 0 && total) *total = carry;
+}
+
+HC_KERNEL HC_LAUNCH_BOUNDS(256, 4)
+gather_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT len,
+              u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u32 nf)
+{
+    const u32 tid = threadIdx.x;
+    for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
+        const u64 n = len[f];
+        const u8 *src = in + in_off[f];
+        u8 *dst = out + out_off[f];
+        for (u64 p = ((u64)blockIdx.x * TPB + tid) * 16; p < n; p += (u64)gridDim.x * TPB * 16) {
+            uint4 v = ldg16(src + p);
+            if (p + 16 > n) v = mask_tail(v, (u32)(n - p));
+            stg16(dst + p, v);
+        }
+    }
+}
+
+// off[f] = f * stride
+HC_KERNEL strided_offsets_kernel(u64 *off, u64 *cap, u64 stride, u32 nf)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nf) { off[i] = (u64)i * stride; if (cap) cap[i] = stride; }
+}
+
+// compress prep: height = len / width, status 6 when -a and len % width != 0 (src/main.cpp:54-59)
+HC_KERNEL compress_prep_kernel(const u64 *HC_RESTRICT len, const u64 *HC_RESTRICT width, u64 *HC_RESTRICT w_eff,
+                               u64 *HC_RESTRICT h_eff, u64 *HC_RESTRICT len_eff, u8 *HC_RESTRICT flags,
+                               i32 *HC_RESTRICT st, u32 nf, int use_diff, int use_adapt)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    u64 w = width ? width[i] : 512, n = len[i];
+    i32 s = 0;
+    u64 h = 0;
+    if (use_adapt) {
+        if (w == 0 || n % w != 0) { s = 6; w = 0; }
+        else h = n / w;
+    }
+    w_eff[i] = w; h_eff[i] = h;
+    len_eff[i] = s ? 0 : n;
+    flags[i] = (u8)(((use_diff ? 1 : 0) << 7) | ((use_adapt ? 1 : 0) << 6));
+    st[i] = s;
+}
+
+// sym_len of files that failed an earlier stage is forced to 0 before FGK
+HC_KERNEL mask_len_kernel(u64 *HC_RESTRICT len, const i32 *HC_RESTRICT st_a, const i32 *HC_RESTRICT st_b, u32 nf)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nf && ((st_a && st_a[i]) || (st_b && st_b[i]))) len[i] = 0;
+}
+
+HC_KERNEL merge_status_kernel(const i32 *HC_RESTRICT a, const i32 *HC_RESTRICT b, const i32 *HC_RESTRICT c,
+                              i32 *HC_RESTRICT st, u64 *HC_RESTRICT out_len, u32 nf)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    i32 s = (a && a[i]) ? a[i] : ((b && b[i]) ? b[i] : (c ? c[i] : 0));
+    st[i] = s;
+    if (s && s != 100 && out_len) out_len[i] = 0;
+}
+
+// decompress: split the FGK-decoded streams by kind (header flag bit 6 / bit 7)
+HC_KERNEL decompress_split_kernel(const u64 *HC_RESTRICT sym_len, const u8 *HC_RESTRICT flags,
+                                  const i32 *HC_RESTRICT st_fgk, u64 *HC_RESTRICT len_plain,
+                                  u64 *HC_RESTRICT len_adapt, u32 nf)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    bool ok = st_fgk[i] == 0, adapt = (flags[i] >> 6) & 1;
+    len_plain[i] = (ok && !adapt) ? sym_len[i] : 0;
+    len_adapt[i] = (ok && adapt) ? sym_len[i] : 0;
+}
+
+HC_KERNEL decompress_merge_kernel(const u8 *HC_RESTRICT flags, const i32 *HC_RESTRICT st_fgk,
+                                  const u64 *HC_RESTRICT n_plain, const i32 *HC_RESTRICT st_plain,
+                                  const u64 *HC_RESTRICT n_adapt, const i32 *HC_RESTRICT st_adapt,
+                                  u64 *HC_RESTRICT out_len, u64 *HC_RESTRICT len_diff, i32 *HC_RESTRICT st, u32 nf)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    bool adapt = (flags[i] >> 6) & 1, diff = (flags[i] >> 7) & 1;
+    i32 s = st_fgk[i];
+    u64 n = 0;
+    if (!s) {
+        s = adapt ? st_adapt[i] : st_plain[i];
+        n = adapt ? n_adapt[i] : n_plain[i];
+    }
+    if (s && s != 100) n = 0;
+    out_len[i] = n;
+    st[i] = s;
+    if (len_diff) len_diff[i] = (!s && diff) ? n : 0;
+}
+
+static inline dim3 grid2(u64 x, u32 nf)
+{
+    if (x == 0) x = 1;
+    if (x > 0x7fffffffull) x = 0x7fffffffull;
+    return dim3((unsigned)x, nf > 65535u ? 65535u : (nf ? nf : 1u));
+}
+
+}  // namespace hcd
+
+using namespace hcd;
+
+// ======================================================================= misc
+extern "C" const char *hc_version(void) { return "hc_b200 0.1 (sm_100a)"; }
+
+extern "C" int hc_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return -(int)e;
+    return n;
+}
+
+extern "C" const char *hc_error_string(int code)
+{
+    if (code < 0) return cudaGetErrorString((cudaError_t)(-code));
+    switch (code) {
+    case 0: return "ok";
+    case 6: return "invalid size of input 2D data detected";
+    case 8: return "invalid or missing Huffman coding header";
+    case 9: return "invalid Huffman coding file contents";
+    case 10: return "invalid or missing adaptive block RLE header";
+    case 11: return "invalid adaptive block RLE header";
+    case 12: return "too small 2D data dimensions";
+    case 13: return "invalid adaptive block RLE file contents";
+    case 14: return "unexpected end of adaptive block RLE data";
+    case 15: return "leftover data of adaptive block RLE detected";
+    case 100: return "output capacity too small";
+    case 101: return "FGK code longer than 56 bits";
+    default: return "unknown";
+    }
+}
+
+extern "C" uint64_t hc_launch_count(void) { return g_launches.load(); }
+
+extern "C" uint64_t hc_rle_bound(uint64_t n) { return n + n / 3 + 4; }
+extern "C" uint64_t hc_block_count(uint64_t w, uint64_t h, uint64_t b)
+{
+    if (b == 0) return 0;
+    return (w / b + (w % b != 0)) * (h / b + (h % b != 0));
+}
+extern "C" uint64_t hc_adapt_bound(uint64_t w, uint64_t h)
+{
+    // header + direction bytes of the finest tiling + 4/3 expansion + one forced literal per block
+    uint64_t nb = hc_block_count(w, h, 8);
+    return 24 + (nb + 7) / 8 + hc_rle_bound(w * h) + 2 * nb;
+}
+extern "C" uint64_t hc_fgk_bound(uint64_t m)
+{
+    // FGK emits at most 2S + m bits (S = optimal static code length <= 8m) plus 256 escapes
+    return 9 + (17 * m + 7) / 8 + 8 * 1024;
+}
+
+// ======================================================================= stage level
+extern "C" int hc_diff_apply_batch(const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
+                                   const uint64_t *len, uint32_t nf, uint64_t max_len, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    u64 tiles = (max_len + TILE_BYTES - 1) / TILE_BYTES;
+    HC_LAUNCH(diff_apply_kernel, grid2(tiles, nf), dim3(TPB), 0, stream, in, in_off, out, out_off, len, nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hc_diff_revert_batch(const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
+                                    const uint64_t *len, uint32_t nf, uint64_t max_len, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    SegPlan p = plan_segments(nf, max_len);
+    u32 *segsum = nullptr;
+    if (p.nseg > 1) {
+        HC_CUDA(cudaMallocAsync((void **)&segsum, (size_t)nf * p.nseg * sizeof(u32), (cudaStream_t)stream));
+        HC_LAUNCH(diff_segsum_kernel, grid2(p.nseg, nf), dim3(TPB), 0, stream, in, in_off, len, nf, p.nseg,
+                  p.seg_bytes, segsum);
+        HC_CHECK_LAUNCH();
+    }
+    HC_LAUNCH(diff_revert_kernel, grid2(p.nseg, nf), dim3(TPB), 0, stream, in, in_off, out, out_off, len, nf,
+              p.nseg, p.seg_bytes, (const u32 *)segsum);
+    HC_CHECK_LAUNCH();
+    if (segsum) HC_CUDA(cudaFreeAsync(segsum, (cudaStream_t)stream));
+    return 0;
+}
+
+static inline unsigned file_grid(uint32_t nf) { return nf > 0x7fffffffu ? 0x7fffffffu : (nf ? nf : 1u); }
+
+extern "C" int hc_rle_encode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                                   uint8_t *out, const uint64_t *out_off, uint64_t *out_len,
+                                   uint32_t nf, uint64_t max_len, hc_stream_t stream)
+{
+    (void)max_len;
+    if (nf == 0) return 0;
+    HC_LAUNCH(rle_encode_kernel, dim3(file_grid(nf)), dim3(TPB), 0, stream, in, in_off, in_len, out, out_off,
+              out_len, nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hc_rle_decode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                                   uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
+                                   uint64_t *out_len, int32_t *status,
+                                   uint32_t nf, uint64_t max_len, hc_stream_t stream)
+{
+    (void)max_len;
+    if (nf == 0) return 0;
+    HC_LAUNCH(rle_decode_kernel, dim3(file_grid(nf)), dim3(TPB), 0, stream, in, in_off, in_len, out, out_off,
+              out_cap, out_len, status, nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+// scratch layout of the adaptive encoder (per file): cost table | block offsets ; then chosen_b
+static inline u64 ad_cost_stride(u64 max_len) { return max_len / 16 + 32; }
+static inline u64 ad_off_stride(u64 max_len) { return max_len / 32 + 16; }
+
+extern "C" uint64_t hc_adapt_encode_ws_bytes(uint32_t nf, uint64_t max_len)
+{
+    return (uint64_t)nf * ((ad_cost_stride(max_len) + ad_off_stride(max_len)) * 4 + 8) + 256;
+}
+
+extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
+                                     const uint64_t *width, const uint64_t *height,
+                                     uint8_t *out, const uint64_t *out_off, uint64_t *out_len,
+                                     uint64_t *chosen_b, int32_t *status,
+                                     uint32_t nf, uint64_t max_len, void *ws, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    const u64 cs = ad_cost_stride(max_len), os = ad_off_stride(max_len);
+    u32 *cost = (u32 *)ws;
+    u32 *boff = cost + (u64)nf * cs;
+    u64 *cb = (u64 *)(((uintptr_t)(boff + (u64)nf * os) + 7) & ~(uintptr_t)7);
+    // work split: enough CTAs to fill 148 SMs, at most one chunk per 64 KiB of image
+    u64 chunks = max_len / (64 * 1024);
+    if (chunks < 1) chunks = 1;
+    u64 want = (592 * 2 + (u64)nf * AD_NCAND - 1) / ((u64)nf * AD_NCAND);
+    if (chunks > want) chunks = want < 1 ? 1 : want;
+    if (chunks > 4096) chunks = 4096;
+    HC_LAUNCH(adapt_cost_kernel, grid2(chunks * AD_NCAND, nf), dim3(AD_COST_TPB), 0, stream, in, in_off, width,
+              height, nf, cost, cs, (u32)chunks);
+    HC_CHECK_LAUNCH();
+    HC_LAUNCH(adapt_select_kernel, dim3(file_grid(nf)), dim3(256), 0, stream, width, height, nf,
+              (const u32 *)cost, cs, boff, os, out, out_off, out_len, cb, status);
+    HC_CHECK_LAUNCH();
+    u64 echunks = max_len / (64 * 1024);
+    if (echunks < 1) echunks = 1;
+    u64 ewant = (592 * 2 + nf - 1) / nf;
+    if (echunks > ewant) echunks = ewant;
+    HC_LAUNCH(adapt_emit_kernel, grid2(echunks, nf), dim3(AD_EMIT_TPB), 0, stream, in, in_off, width, height, nf,
+              (const u32 *)cost, cs, (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status);
+    HC_CHECK_LAUNCH();
+    if (chosen_b)
+        HC_CUDA(cudaMemcpyAsync(chosen_b, cb, (size_t)nf * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" uint64_t hc_adapt_decode_ws_bytes(uint32_t nf, uint64_t max_out_len)
+{
+    (void)nf; (void)max_out_len;
+    return 256;   // v1 decoder needs no scratch
+}
+
+extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                                     uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
+                                     uint64_t *out_len, int32_t *status,
+                                     uint32_t nf, uint64_t max_in_len, uint64_t max_out_len,
+                                     void *ws, hc_stream_t stream)
+{
+    (void)max_in_len; (void)max_out_len; (void)ws;
+    if (nf == 0) return 0;
+    HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off,
+              out_cap, out_len, status, nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hc_fgk_encode_batch(const uint8_t *sym, const uint64_t *sym_off, const uint64_t *sym_len,
+                                   const uint8_t *flags,
+                                   uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
+                                   uint64_t *out_len, int32_t *status,
+                                   uint32_t nf, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    HC_LAUNCH(fgk_encode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, sym,
+              sym_off, sym_len, flags, out, out_off, out_cap, out_len, status, nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hc_fgk_decode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                                   uint8_t *sym, const uint64_t *sym_off, const uint64_t *sym_cap,
+                                   uint64_t *sym_len, uint8_t *flags, int32_t *status,
+                                   uint32_t nf, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    HC_LAUNCH(fgk_decode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, in,
+              in_off, in_len, sym, sym_off, sym_cap, sym_len, flags, status, nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hc_offsets_from_lens(const uint64_t *len, uint64_t *out_off, uint64_t *total,
+                                    uint32_t nf, uint32_t align, hc_stream_t stream)
+{
+    if (align == 0) align = 1;
+    HC_LAUNCH(offsets_scan_kernel, dim3(1), dim3(TPB), 0, stream, len, out_off, total, nf, align);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hc_gather_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *len,
+                               uint8_t *out, const uint64_t *out_off,
+                               uint32_t nf, uint64_t max_len, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    u64 x = (max_len + TPB * 16 * 4 - 1) / (TPB * 16 * 4);
+    HC_LAUNCH(gather_kernel, grid2(x, nf), dim3(TPB), 0, stream, in, in_off, len, out, out_off, nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+// ======================================================================= codec (host level)
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return -(int)e;
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, n + 4096, cudaHostAllocDefault);
+        if (e != cudaSuccess) return -(int)e;
+        cap = n + 4096;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+#define HC_MAX_STAGES 16
+
+struct hc_codec {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf in, a, b, out, tab, ws;      // raw input, stage buffers, strided output, tables, scratch
+    HostBuf htab;
+    bool timing = false;
+    cudaEvent_t ev[HC_MAX_STAGES + 1];
+    const char *stage_names[HC_MAX_STAGES];
+    int nstages = 0;
+    bool ev_ready = false;
+};
+
+#define HC_TRY(x)                  \
+    do {                           \
+        int r_ = (x);              \
+        if (r_ != 0) return r_;    \
+    } while (0)
+
+static void stage_begin(hc_codec *c)
+{
+    c->nstages = 0;
+    if (c->timing) cudaEventRecord(c->ev[0], c->stream);
+}
+static void stage_mark(hc_codec *c, const char *name)
+{
+    if (!c->timing || c->nstages >= HC_MAX_STAGES) return;
+    c->stage_names[c->nstages] = name;
+    c->nstages++;
+    cudaEventRecord(c->ev[c->nstages], c->stream);
+}
+
+extern "C" int hc_codec_create(hc_codec **out, int device)
+{
+    int n = hc_device_count();
+    if (n < 0) return n;
+    if (n == 0 || device >= n) return -100;     // cudaErrorNoDevice
+    HC_CUDA(cudaSetDevice(device));
+    hc_codec *c = new hc_codec();
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return -(int)e; }
+    for (int i = 0; i <= HC_MAX_STAGES; i++) cudaEventCreate(&c->ev[i]);
+    c->ev_ready = true;
+    *out = c;
+    return 0;
+}
+
+extern "C" void hc_codec_destroy(hc_codec *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release();
+    c->htab.release();
+    if (c->ev_ready) for (int i = 0; i <= HC_MAX_STAGES; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" void *hc_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void hc_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" hc_stream_t hc_codec_stream(hc_codec *c) { return (hc_stream_t)c->stream; }
+extern "C" void hc_codec_enable_stage_timing(hc_codec *c, int on) { c->timing = on != 0; }
+extern "C" const char *hc_stage_name(hc_codec *c, int i) { return (i >= 0 && i < c->nstages) ? c->stage_names[i] : ""; }
+extern "C" int hc_codec_stage_times(hc_codec *c, float *ms, int max_stages)
+{
+    if (!c->timing) return 0;
+    int n = c->nstages < max_stages ? c->nstages : max_stages;
+    for (int i = 0; i < n; i++) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]) != cudaSuccess) return -1;
+        ms[i] = t;
+    }
+    return n;
+}
+
+static inline unsigned blocks_for(u32 nf) { return (nf + 255) / 256; }
+
+// device table slots inside c->tab (each nf elements)
+struct TabView {
+    u8 *base;
+    u32 nf;
+    u64 *u64_at(int slot) const { return (u64 *)(base + (size_t)slot * nf * 8); }
+    i32 *i32_at(int slot) const { return (i32 *)(base + (size_t)slot * nf * 8); }
+    u8 *u8_at(int slot) const { return base + (size_t)slot * nf * 8; }
+};
+enum { T_OFF_A = 0, T_CAP_A, T_LEN_A, T_OFF_B, T_CAP_B, T_LEN_B, T_W, T_H, T_LEN_EFF, T_FLAGS, T_ST0, T_ST1, T_ST2,
+       T_LEN_P, T_LEN_AD, T_N_P, T_N_AD, T_LEN_DIFF, T_CB, T_USER0, T_USER1, T_USER2, T_USER3, T_USER4, T_NSLOTS };
+
+// worst-case adaptive output when only w*h = n is known (nb <= n/32 + 2 for w, h >= 8)
+static inline u64 adapt_bound_from_len(u64 n) { return 24 + n / 256 + 8 + n + n / 3 + 4 * (n / 32 + 2) + 16; }
+
+extern "C" int hc_compress_device(hc_codec *c, const uint8_t *d_in, const uint64_t *d_in_off,
+                                  const uint64_t *d_in_len, const uint64_t *d_width,
+                                  uint32_t nf, uint64_t max_len, int use_diff, int use_adapt,
+                                  uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap,
+                                  uint64_t *d_out_len, int32_t *d_status)
+{
+    if (nf == 0) return 0;
+    HC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    HC_TRY(c->tab.ensure((size_t)T_NSLOTS * nf * 8));
+    TabView t{(u8 *)c->tab.p, nf};
+    const u64 stride_a = align_up(max_len + 16, HC_ALIGN);
+    const u64 bound_b = use_adapt ? adapt_bound_from_len(max_len) : hc_rle_bound(max_len);
+    const u64 stride_b = align_up(bound_b + 16, HC_ALIGN);
+    if (use_diff) HC_TRY(c->a.ensure((size_t)stride_a * nf));
+    HC_TRY(c->b.ensure((size_t)stride_b * nf));
+    if (use_adapt) HC_TRY(c->ws.ensure((size_t)hc_adapt_encode_ws_bytes(nf, max_len)));
+
+    stage_begin(c);
+    HC_LAUNCH(strided_offsets_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, t.u64_at(T_OFF_A), t.u64_at(T_CAP_A), stride_a, nf);
+    HC_LAUNCH(strided_offsets_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, t.u64_at(T_OFF_B), t.u64_at(T_CAP_B), stride_b, nf);
+    HC_LAUNCH(compress_prep_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, d_in_len, d_width, t.u64_at(T_W), t.u64_at(T_H),
+              t.u64_at(T_LEN_EFF), t.u8_at(T_FLAGS), t.i32_at(T_ST0), nf, use_diff, use_adapt);
+    HC_CHECK_LAUNCH();
+    stage_mark(c, "prep");
+
+    const u8 *cur = d_in;
+    const u64 *cur_off = d_in_off;
+    const u64 *len_eff = t.u64_at(T_LEN_EFF);
+    if (use_diff) {
+        HC_TRY(hc_diff_apply_batch(cur, cur_off, (u8 *)c->a.p, t.u64_at(T_OFF_A), len_eff, nf, max_len, s));
+        cur = (const u8 *)c->a.p;
+        cur_off = t.u64_at(T_OFF_A);
+        stage_mark(c, "diff_apply");
+    }
+    i32 *st1 = nullptr;
+    if (use_adapt) {
+        // files rejected by prep (status 6) carry width 0 -> the adaptive stage reports 12 for
+        // them; the prep status wins in the merge below
+        st1 = t.i32_at(T_ST1);
+        HC_TRY(hc_adapt_encode_batch(cur, cur_off, t.u64_at(T_W), t.u64_at(T_H), (u8 *)c->b.p, t.u64_at(T_OFF_B),
+                                     t.u64_at(T_LEN_B), nullptr, st1, nf, max_len, c->ws.p, s));
+        stage_mark(c, "adapt_encode");
+    } else {
+        HC_TRY(hc_rle_encode_batch(cur, cur_off, len_eff, (u8 *)c->b.p, t.u64_at(T_OFF_B), t.u64_at(T_LEN_B), nf, max_len, s));
+        stage_mark(c, "rle_encode");
+    }
+    HC_LAUNCH(mask_len_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, t.u64_at(T_LEN_B), (const i32 *)t.i32_at(T_ST0),
+              (const i32 *)st1, nf);
+    HC_CHECK_LAUNCH();
+    HC_TRY(hc_fgk_encode_batch((const u8 *)c->b.p, t.u64_at(T_OFF_B), t.u64_at(T_LEN_B), t.u8_at(T_FLAGS), d_out, d_out_off,
+                               d_out_cap, d_out_len, t.i32_at(T_ST2), nf, s));
+    stage_mark(c, "fgk_encode");
+    HC_LAUNCH(merge_status_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, (const i32 *)t.i32_at(T_ST0), (const i32 *)st1,
+              (const i32 *)t.i32_at(T_ST2), d_status, d_out_len, nf);
+    HC_CHECK_LAUNCH();
+    stage_mark(c, "merge");
+    return 0;
+}
+
+// stage 1 of decompression: header parse + FGK decode into c->a (strided), split by kind
+static int dec_fgk(hc_codec *c, const uint8_t *d_in, const uint64_t *d_in_off, const uint64_t *d_in_len,
+                   uint32_t nf, uint64_t max_sym_len)
+{
+    cudaStream_t s = c->stream;
+    HC_TRY(c->tab.ensure((size_t)T_NSLOTS * nf * 8));
+    TabView t{(u8 *)c->tab.p, nf};
+    const u64 stride_a = align_up(max_sym_len + 16, HC_ALIGN);
+    HC_TRY(c->a.ensure((size_t)stride_a * nf));
+    HC_LAUNCH(strided_offsets_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, t.u64_at(T_OFF_A), t.u64_at(T_CAP_A), stride_a, nf);
+    HC_CHECK_LAUNCH();
+    HC_TRY(hc_fgk_decode_batch(d_in, d_in_off, d_in_len, (u8 *)c->a.p, t.u64_at(T_OFF_A), t.u64_at(T_CAP_A), t.u64_at(T_LEN_A),
+                               t.u8_at(T_FLAGS), t.i32_at(T_ST0), nf, s));
+    stage_mark(c, "fgk_decode");
+    HC_LAUNCH(decompress_split_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, (const u64 *)t.u64_at(T_LEN_A),
+              (const u8 *)t.u8_at(T_FLAGS), (const i32 *)t.i32_at(T_ST0), t.u64_at(T_LEN_P), t.u64_at(T_LEN_AD), nf);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
+// stage 2: RLE / adaptive expansion (+ diff revert) of the symbol streams left in c->a.
+// d_out == NULL only computes sizes and statuses.
+static int dec_expand(hc_codec *c, uint32_t nf, uint64_t max_sym_len, uint64_t max_out_len, int kinds,
+                      uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap,
+                      uint64_t *d_out_len, int32_t *d_status)
+{
+    cudaStream_t s = c->stream;
+    TabView t{(u8 *)c->tab.p, nf};
+    HC_CUDA(cudaMemsetAsync(t.u64_at(T_N_P), 0, (size_t)nf * 8, s));
+    HC_CUDA(cudaMemsetAsync(t.u64_at(T_N_AD), 0, (size_t)nf * 8, s));
+    HC_CUDA(cudaMemsetAsync(t.i32_at(T_ST1), 0, (size_t)nf * 8, s));
+    HC_CUDA(cudaMemsetAsync(t.i32_at(T_ST2), 0, (size_t)nf * 8, s));
+    if (kinds & HC_KIND_PLAIN) {
+        HC_TRY(hc_rle_decode_batch((const u8 *)c->a.p, t.u64_at(T_OFF_A), t.u64_at(T_LEN_P), d_out, d_out_off, d_out_cap,
+                                   t.u64_at(T_N_P), t.i32_at(T_ST1), nf, max_sym_len, s));
+        stage_mark(c, d_out ? "rle_decode" : "rle_decode_size");
+    }
+    if (kinds & HC_KIND_ADAPT) {
+        // non-adaptive files carry length 0 here (status 10 for them is ignored by the merge)
+        HC_TRY(hc_adapt_decode_batch((const u8 *)c->a.p, t.u64_at(T_OFF_A), t.u64_at(T_LEN_AD), d_out, d_out_off, d_out_cap,
+                                     t.u64_at(T_N_AD), t.i32_at(T_ST2), nf, max_sym_len, max_out_len, nullptr, s));
+        stage_mark(c, d_out ? "adapt_decode" : "adapt_decode_size");
+    }
+    HC_LAUNCH(decompress_merge_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, (const u8 *)t.u8_at(T_FLAGS),
+              (const i32 *)t.i32_at(T_ST0), (const u64 *)t.u64_at(T_N_P), (const i32 *)t.i32_at(T_ST1),
+              (const u64 *)t.u64_at(T_N_AD), (const i32 *)t.i32_at(T_ST2), d_out_len, t.u64_at(T_LEN_DIFF), d_status, nf);
+    HC_CHECK_LAUNCH();
+    if ((kinds & HC_KIND_DIFF) && d_out) {
+        HC_TRY(hc_diff_revert_batch(d_out, d_out_off, d_out, d_out_off, t.u64_at(T_LEN_DIFF), nf, max_out_len, s));
+        stage_mark(c, "diff_revert");
+    }
+    return 0;
+}
+
+extern "C" int hc_decompress_device(hc_codec *c, const uint8_t *d_in, const uint64_t *d_in_off,
+                                    const uint64_t *d_in_len, uint32_t nf,
+                                    uint64_t max_sym_len, uint64_t max_out_len, int kinds,
+                                    uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap,
+                                    uint64_t *d_out_len, int32_t *d_status)
+{
+    if (nf == 0) return 0;
+    HC_CUDA(cudaSetDevice(c->device));
+    if (kinds == 0) kinds = HC_KIND_PLAIN | HC_KIND_ADAPT | HC_KIND_DIFF;
+    stage_begin(c);
+    HC_TRY(dec_fgk(c, d_in, d_in_off, d_in_len, nf, max_sym_len));
+    return dec_expand(c, nf, max_sym_len, max_out_len, kinds, d_out, d_out_off, d_out_cap, d_out_len, d_status);
+}
+
+// ---------------------------------------------------------------------- host buffers in / out
+// Upload nf host files.  If the caller's layout is already vector friendly (16-byte aligned
+// starts, dense, non-overlapping 16-byte slots) it is copied with ONE cudaMemcpyAsync and used
+// as is; otherwise every file is copied into a 256-byte aligned packed layout.
+static int upload_files(hc_codec *c, DevBuf &dst, const uint8_t *base, const uint64_t *off, const uint64_t *len,
+                        uint32_t nf, std::vector<u64> &d_off)
+{
+    u64 lo = ~0ull, hi = 0, sum = 0;
+    bool direct = true;
+    for (u32 i = 0; i < nf; i++) {
+        if (off[i] % 16) direct = false;
+        if (off[i] < lo) lo = off[i];
+        if (off[i] + len[i] > hi) hi = off[i] + len[i];
+        sum += len[i];
+        if (i + 1 < nf && (off[i + 1] < off[i] || off[i] + align_up(len[i], 16) > off[i + 1])) direct = false;
+    }
+    if (nf == 0) lo = hi = 0;
+    if (hi - lo > sum + sum / 2 + (u64)nf * 256) direct = false;      // too sparse: re-pack
+    d_off.resize(nf);
+    if (direct) {
+        HC_TRY(dst.ensure((size_t)(hi - lo) + 512));
+        if (hi > lo) HC_CUDA(cudaMemcpyAsync(dst.p, base + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
+        for (u32 i = 0; i < nf; i++) d_off[i] = off[i] - lo;
+    } else {
+        u64 pos = 0;
+        for (u32 i = 0; i < nf; i++) { d_off[i] = pos; pos += align_up(len[i] + 16, HC_ALIGN); }
+        HC_TRY(dst.ensure((size_t)pos + 512));
+        for (u32 i = 0; i < nf; i++)
+            if (len[i])
+                HC_CUDA(cudaMemcpyAsync((u8 *)dst.p + d_off[i], base + off[i], (size_t)len[i], cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
+}
+
+struct AsyncFree {   // stream-ordered scratch released on every exit path
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    ~AsyncFree() { if (p) cudaFreeAsync(p, s); }
+};
+
+extern "C" int hc_compress_batch(hc_codec *c,
+                                 const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                 uint32_t nf, int use_diff, int use_adapt, const uint64_t *width_host,
+                                 uint8_t *out_base, uint64_t out_cap_total,
+                                 uint64_t *out_off, uint64_t *out_len, int32_t *status)
+{
+    if (nf == 0) return 0;
+    HC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    std::vector<u64> d_off;
+    HC_TRY(upload_files(c, c->in, in_base, in_off, in_len, nf, d_off));
+
+    // pinned host tables, 7 x nf: in_off | in_len | width | out_off (strided) | out_cap | compact off | compact len
+    HC_TRY(c->htab.ensure((size_t)nf * 8 * 7));
+    u64 *h = (u64 *)c->htab.p;
+    const size_t N = nf;
+    u64 max_len = 0, pos = 0;
+    for (u32 i = 0; i < nf; i++) {
+        h[i] = d_off[i];
+        h[N + i] = in_len[i];
+        if (in_len[i] > max_len) max_len = in_len[i];
+        u64 w = width_host ? width_host[i] : 512;
+        h[2 * N + i] = w;
+        u64 m_bound = use_adapt ? adapt_bound_from_len(in_len[i]) : hc_rle_bound(in_len[i]);
+        u64 cap = align_up(hc_fgk_bound(m_bound) + 16, HC_ALIGN);
+        h[3 * N + i] = pos;
+        h[4 * N + i] = cap;
+        pos += cap;
+    }
+    HC_TRY(c->out.ensure((size_t)pos + 512));
+    AsyncFree dev;
+    dev.s = s;
+    HC_CUDA(cudaMallocAsync(&dev.p, N * 8 * 9, s));       // 7 tables + out_len + status
+    u64 *d = (u64 *)dev.p;
+    u64 *d_out_len = d + 7 * N;
+    i32 *d_status = (i32 *)(d + 8 * N);
+    HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 5, cudaMemcpyHostToDevice, s));
+    HC_TRY(hc_compress_device(c, (const u8 *)c->in.p, d, d + N, d + 2 * N, nf, max_len, use_diff, use_adapt,
+                              (u8 *)c->out.p, d + 3 * N, d + 4 * N, d_out_len, d_status));
+    HC_CUDA(cudaMemcpyAsync(out_len, d_out_len, N * 8, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaMemcpyAsync(status, d_status, N * 4, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    // compact layout: files back to back, starts aligned to 16 bytes
+    u64 total = 0, max_out = 0;
+    for (u32 i = 0; i < nf; i++) {
+        u64 n = status[i] == 0 ? out_len[i] : 0;
+        if (status[i] != 0 && status[i] != HC_E_CAPACITY) out_len[i] = 0;
+        out_off[i] = total;
+        h[5 * N + i] = total;
+        h[6 * N + i] = n;
+        if (n > max_out) max_out = n;
+        total += align_up(n, 16);
+    }
+    if (total > out_cap_total) return HC_E_CAPACITY;
+    // gather strided -> compact on the device, then ONE device-to-host copy
+    HC_TRY(c->a.ensure((size_t)total + 512));
+    HC_CUDA(cudaMemcpyAsync(d + 5 * N, h + 5 * N, N * 8 * 2, cudaMemcpyHostToDevice, s));
+    HC_TRY(hc_gather_batch((const u8 *)c->out.p, d + 3 * N, d + 6 * N, (u8 *)c->a.p, d + 5 * N, nf, max_out, s));
+    if (total) HC_CUDA(cudaMemcpyAsync(out_base, c->a.p, (size_t)total, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int hc_decompress_batch(hc_codec *c,
+                                   const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                   uint32_t nf,
+                                   uint8_t *out_base, uint64_t out_cap_total,
+                                   uint64_t *out_off, uint64_t *out_len, int32_t *status)
+{
+    if (nf == 0) return 0;
+    HC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    std::vector<u64> d_off;
+    HC_TRY(upload_files(c, c->in, in_base, in_off, in_len, nf, d_off));
+    // header peek on the host: symbol counts size the FGK output, flag bytes select the kernels
+    u64 max_sym = 0;
+    int kinds = 0;
+    for (u32 i = 0; i < nf; i++) {
+        if (in_len[i] < 9) continue;
+        const u8 *p = in_base + in_off[i];
+        u64 m = 0;
+        for (int k = 0; k < 8; k++) m |= (u64)p[k] << (8 * k);
+        if (m > (in_len[i] - 9) * 8 + 1) m = 0;            // cannot decode: the kernel reports 9
+        if (m > max_sym) max_sym = m;
+        kinds |= (p[8] & 0x40) ? HC_KIND_ADAPT : HC_KIND_PLAIN;
+        if (p[8] & 0x80) kinds |= HC_KIND_DIFF;
+    }
+    if ((kinds & (HC_KIND_PLAIN | HC_KIND_ADAPT)) == 0) kinds |= HC_KIND_PLAIN;
+    // pinned tables, 4 x nf: in_off | in_len | out_off | out_cap
+    HC_TRY(c->htab.ensure((size_t)nf * 8 * 4));
+    u64 *h = (u64 *)c->htab.p;
+    const size_t N = nf;
+    for (u32 i = 0; i < nf; i++) { h[i] = d_off[i]; h[N + i] = in_len[i]; }
+    AsyncFree dev;
+    dev.s = s;
+    HC_CUDA(cudaMallocAsync(&dev.p, N * 8 * 6, s));
+    u64 *d = (u64 *)dev.p;
+    u64 *d_out_len = d + 4 * N;
+    i32 *d_status = (i32 *)(d + 5 * N);
+    HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 2, cudaMemcpyHostToDevice, s));
+    // pass 1: FGK decode, then sizes only
+    stage_begin(c);
+    HC_TRY(dec_fgk(c, (const u8 *)c->in.p, d, d + N, nf, max_sym));
+    HC_TRY(dec_expand(c, nf, max_sym, 0, kinds, nullptr, nullptr, nullptr, d_out_len, d_status));
+    HC_CUDA(cudaMemcpyAsync(out_len, d_out_len, N * 8, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaMemcpyAsync(status, d_status, N * 4, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    u64 total = 0, max_out = 0;
+    for (u32 i = 0; i < nf; i++) {
+        u64 n = status[i] == 0 ? out_len[i] : 0;
+        out_off[i] = total;
+        h[2 * N + i] = total;
+        h[3 * N + i] = align_up(n, 16);
+        if (n > max_out) max_out = n;
+        total += align_up(n, 16);
+    }
+    if (total > out_cap_total) return HC_E_CAPACITY;
+    HC_TRY(c->out.ensure((size_t)total + 512));
+    HC_CUDA(cudaMemcpyAsync(d + 2 * N, h + 2 * N, N * 8 * 2, cudaMemcpyHostToDevice, s));
+    // pass 2: expansion straight into the compact layout (the FGK result of pass 1 is reused)
+    HC_TRY(dec_expand(c, nf, max_sym, max_out, kinds, (u8 *)c->out.p, d + 2 * N, d + 3 * N, d_out_len, d_status));
+    HC_CUDA(cudaMemcpyAsync(out_len, d_out_len, N * 8, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaMemcpyAsync(status, d_status, N * 4, cudaMemcpyDeviceToHost, s));
+    if (total) HC_CUDA(cudaMemcpyAsync(out_base, c->out.p, (size_t)total, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    for (u32 i = 0; i < nf; i++)
+        if (status[i] != 0) out_len[i] = 0;
+    return 0;
+}

@@ -1,0 +1,160 @@
+"""Whole-file parity through the host-level C ABI (hc_compress_batch / hc_decompress_batch
+= huffCompress / huffDecompress, reference src/main.cpp:39-128).
+
+Compared against: the CPU oracle, the golden digests produced by the unmodified reference
+binary (tests/golden/golden.json) and -- when oracle/_ref travelled with the snapshot -- the
+reference binary itself in both directions (ours -> ref -d, ref -c -> ours).
+"""
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import hc_b200
+import pyoracle
+import synth
+from backend import CudaBackend, EmuBackend
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+_cache = {}
+MODES = {"plain": (False, False), "m": (True, False), "a": (False, True), "ma": (True, True)}
+
+
+@pytest.fixture(params=BACKENDS)
+def codec(request):
+    name = request.param
+    if name not in _cache:
+        be = EmuBackend() if name == "emu" else CudaBackend()
+        _cache[name] = (hc_b200.Codec(0, be.L), name)
+    return _cache[name]
+
+
+def _sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def test_a7_vectors(codec, golden):
+    cd, _ = codec
+    for v in golden["a7"]:
+        data = np.frombuffer(bytes.fromhex(v["in"]), np.uint8)
+        f = v["flags"]
+        width = int(f[f.index("-w") + 1]) if "-w" in f else 512
+        outs, st = cd.compress([data], diff="-m" in f, adapt="-a" in f, width=width)
+        assert st[0] == 0 and bytes(outs[0]).hex() == v["out"], v
+        back, st = cd.decompress(outs)
+        assert st[0] == 0 and np.array_equal(back[0], data)
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_small_batch_vs_oracle(codec, oracle, mode):
+    cd, name = codec
+    diff, adapt = MODES[mode]
+    n = 32 if name == "emu" else 96
+    files = []
+    for i, k in enumerate(synth.CLASSES + ("fib", "longrun")):
+        files.append(synth.image(k, n, 400 + i, n + 8 * (i % 3)).reshape(-1))
+    if not adapt:
+        files += [np.zeros(0, np.uint8), np.array([7], np.uint8), np.arange(1000, dtype=np.uint32).astype(np.uint8)[:999]]
+    outs, st = cd.compress(files, diff=diff, adapt=adapt, width=n)
+    assert not st.any()
+    for f, o in zip(files, outs):
+        rc, exp = oracle.compress(f, diff=diff, adapt=adapt, width=n)
+        assert rc == 0 and np.array_equal(o, exp)
+    back, st = cd.decompress(outs)
+    assert not st.any()
+    for f, b in zip(files, back):
+        assert np.array_equal(b, f)
+
+
+def test_mixed_kinds_in_one_decode_batch(codec, oracle):
+    cd, _ = codec
+    img = synth.image("walk", 32, 9, 40).reshape(-1)
+    outs = [oracle.compress(img, diff=d, adapt=a, width=32)[1] for d in (0, 1) for a in (0, 1)]
+    back, st = cd.decompress(outs)
+    assert not st.any()
+    for b in back:
+        assert np.array_equal(b, img)
+
+
+def test_compress_errors(codec):
+    cd, _ = codec
+    files = [np.arange(30, dtype=np.uint8), np.arange(64, dtype=np.uint8), np.arange(35, dtype=np.uint8)]
+    outs, st = cd.compress(files, adapt=True, width=[7, 8, 5])
+    assert list(st) == [6, 0, 12]            # src/main.cpp:54-58, ok, src/transform.cpp:300-304
+    assert outs[0].size == 0 and outs[2].size == 0 and outs[1].size > 9
+    outs, st = cd.compress([np.zeros(0, np.uint8)], adapt=True, width=512)
+    assert list(st) == [12]                  # empty file with -a
+
+
+def test_decompress_errors(codec, golden, oracle):
+    cd, _ = codec
+    blobs, expect = [], []
+    for c in golden["cli"]:
+        if "malformed" in c:
+            blobs.append(np.frombuffer(bytes.fromhex(c["blob"]), np.uint8))
+            expect.append(c["rc"])
+    good = oracle.compress(np.frombuffer(b"hello world, hello world", np.uint8))[1]
+    blobs.append(good)
+    expect.append(0)
+    blobs.append(np.concatenate([good, np.array([1, 2, 3, 4], np.uint8)]))     # trailing bytes are ignored
+    expect.append(0)
+    back, st = cd.decompress(blobs)
+    assert list(st) == expect
+    assert bytes(back[-1]) == b"hello world, hello world" and bytes(back[-2]) == bytes(back[-1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", list(MODES))
+def test_samples_golden(golden, samples, mode):
+    """BASELINE config 2: data/*.raw, all four flag sets, byte identical to the reference."""
+    cd = hc_b200.Codec(0)
+    diff, adapt = MODES[mode]
+    names = sorted(samples)
+    outs, st = cd.compress([samples[n] for n in names], diff=diff, adapt=adapt, width=512)
+    assert not st.any()
+    for n, o in zip(names, outs):
+        g = golden["samples"][n][mode]
+        assert (o.size, _sha(o)) == (g["size"], g["sha256"]), (n, mode)
+    back, st = cd.decompress(outs)
+    assert not st.any()
+    for n, b in zip(names, back):
+        assert _sha(b) == golden["samples"][n]["in_sha256"]
+
+
+@pytest.mark.gpu
+def test_synthetic_golden(golden):
+    cd = hc_b200.Codec(0)
+    for e in golden["synthetic"]:
+        w, h = e.get("w", e.get("n")), e.get("h", e.get("n"))
+        img = synth.image(e["kind"], w, e["seed"], h).reshape(-1)
+        outs, st = cd.compress([img], diff="m" in e["mode"], adapt="a" in e["mode"], width=w)
+        assert st[0] == 0 and (outs[0].size, _sha(outs[0])) == (e["size"], e["sha256"]), e
+
+
+@pytest.mark.gpu
+def test_cross_decode_with_reference_binary(samples):
+    """ours -> reference -d, and reference -c -> ours (only where oracle/_ref is present)."""
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    cd = hc_b200.Codec(0)
+    files = {"hd01": samples["hd01"], "extra": samples["hd01extra"], "walk": synth.image("walk", 200, 5, 120).reshape(-1)}
+    widths = {"hd01": 512, "extra": 512, "walk": 200}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, data in files.items():
+            for flags in ([], ["-m"], ["-a", "-w", str(widths[name])], ["-m", "-a", "-w", str(widths[name])]):
+                ours, st = cd.compress([data], diff="-m" in flags, adapt="-a" in flags, width=widths[name])
+                assert st[0] == 0
+                p_in, p_out, p_dec = (os.path.join(tmp, x) for x in ("in.raw", "o.out", "o.dec"))
+                open(p_out, "wb").write(bytes(ours[0]))
+                r = subprocess.run([pyoracle.REF_BIN, "-d", "-i", p_out, "-o", p_dec], capture_output=True)
+                assert r.returncode == 0 and open(p_dec, "rb").read() == bytes(data)
+                open(p_in, "wb").write(bytes(data))
+                r = subprocess.run([pyoracle.REF_BIN, "-c"] + flags + ["-i", p_in, "-o", p_out], capture_output=True)
+                assert r.returncode == 0
+                ref_out = np.frombuffer(open(p_out, "rb").read(), np.uint8)
+                assert np.array_equal(ref_out, ours[0])
+                back, st = cd.decompress([ref_out])
+                assert st[0] == 0 and np.array_equal(back[0], data)

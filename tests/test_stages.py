@@ -1,0 +1,326 @@
+"""Stage-level parity: every C-ABI stage against the CPU oracle on the same inputs.
+
+Each test runs twice: on the SIMT-emulated kernels (`emu`, CPU box, small inputs) and on the
+real sm_100a kernels (`cuda`, marked gpu).  Bit-exact is the bar everywhere (byte/integer work).
+"""
+import numpy as np
+import pytest
+
+import hc_b200
+import synth
+from backend import Batch, CudaBackend, EmuBackend
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+_cache = {}
+
+
+@pytest.fixture(params=BACKENDS)
+def be(request):
+    name = request.param
+    if name not in _cache:
+        _cache[name] = EmuBackend() if name == "emu" else CudaBackend()
+    return _cache[name]
+
+
+def rc0(rc):
+    assert rc == 0, rc
+
+
+def ragged_files(be, seed=1):
+    """Ragged batch: empty, tiny, vector/tile boundary sizes, run-heavy, count-byte-heavy."""
+    rng = np.random.default_rng(seed)
+    big = 70000 if be.name == "cuda" else 33000
+    sizes = [0, 1, 2, 3, 4, 15, 16, 17, 31, 257, 258, 259, 260, 4095, 4096, 4097, 16383, 16384, 16385, big]
+    files = []
+    for i, n in enumerate(sizes):
+        k = i % 6
+        if k == 0:
+            v = rng.integers(0, 256, n)
+        elif k == 1:
+            reps = rng.integers(1, 700, n // 50 + 2)
+            v = np.repeat(rng.integers(0, 256, reps.size), reps)[:n]
+        elif k == 2:
+            reps = rng.integers(1, 6, n // 2 + 2)
+            v = np.repeat(rng.integers(250, 256, reps.size), reps)[:n]
+        elif k == 3:
+            v = np.full(n, 7)
+        elif k == 4:
+            v = rng.integers(0, 2, n) * 3
+        else:
+            v = np.cumsum(rng.integers(-1, 2, n)) & 255
+        files.append(v.astype(np.uint8))
+    # runs that cross tile (16 KiB) and vector boundaries with lengths around 258*k
+    v = np.concatenate([np.full(16384 - 100, 1), np.full(258 * 3 + 2, 9), np.full(5, 2), np.full(258, 4), np.full(257, 5),
+                        np.full(259, 6), np.arange(40) & 255, np.full(3, 8), np.full(3, 9)]).astype(np.uint8)
+    files.append(v)
+    return files
+
+
+def test_diff_apply_revert(be, oracle):
+    files = ragged_files(be)
+    src = Batch(be, [f.size for f in files], files)
+    dst = Batch(be, [f.size for f in files])
+    rc0(be.L.hc_diff_apply_batch(src.data.ptr, src.d_off.ptr, dst.data.ptr, dst.d_off.ptr, src.d_len.ptr,
+                                 src.nf, src.max_len, be.stream))
+    lens = [f.size for f in files]
+    got = dst.files(lens)
+    for f, g in zip(files, got):
+        assert np.array_equal(g, oracle.diff_apply(f))
+    # revert, out of place and in place
+    back = Batch(be, lens)
+    rc0(be.L.hc_diff_revert_batch(dst.data.ptr, dst.d_off.ptr, back.data.ptr, back.d_off.ptr, src.d_len.ptr,
+                                  src.nf, src.max_len, be.stream))
+    for f, g in zip(files, back.files(lens)):
+        assert np.array_equal(g, f)
+    rc0(be.L.hc_diff_revert_batch(dst.data.ptr, dst.d_off.ptr, dst.data.ptr, dst.d_off.ptr, src.d_len.ptr,
+                                  src.nf, src.max_len, be.stream))
+    for f, g in zip(files, dst.files(lens)):
+        assert np.array_equal(g, f)
+
+
+def test_diff_revert_segmented(be, oracle):
+    # few large files -> the launcher splits each file into segments (per-segment sums + carry)
+    n = 300000 if be.name == "cuda" else 150000
+    rng = np.random.default_rng(3)
+    files = [rng.integers(0, 256, n, dtype=np.uint8), rng.integers(0, 256, n - 12345, dtype=np.uint8)]
+    src = Batch(be, [f.size for f in files], files)
+    dst = Batch(be, [f.size for f in files])
+    rc0(be.L.hc_diff_revert_batch(src.data.ptr, src.d_off.ptr, dst.data.ptr, dst.d_off.ptr, src.d_len.ptr,
+                                  src.nf, src.max_len, be.stream))
+    for f, g in zip(files, dst.files([f.size for f in files])):
+        assert np.array_equal(g, oracle.diff_revert(f))
+
+
+def test_rle_encode(be, oracle):
+    files = ragged_files(be, 2)
+    src = Batch(be, [f.size for f in files], files)
+    dst = Batch(be, [be.L.hc_rle_bound(f.size) for f in files], fill=0xEE)
+    rc0(be.L.hc_rle_encode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_len.ptr,
+                                 src.nf, src.max_len, be.stream))
+    lens = dst.lens()
+    got = dst.files(lens)
+    for i, (f, g) in enumerate(zip(files, got)):
+        exp = oracle.rle_encode(f)
+        assert int(lens[i]) == exp.size, (i, f.size)
+        assert np.array_equal(g, exp), (i, f.size)
+
+
+def test_rle_decode(be, oracle):
+    files = ragged_files(be, 5)
+    encs = [oracle.rle_encode(f) for f in files]
+    # any byte string is a valid MNP-5 stream: also decode raw noise and count-heavy streams
+    rng = np.random.default_rng(11)
+    encs.append(rng.integers(0, 256, 3000, dtype=np.uint8))
+    encs.append(np.tile(np.array([5, 5, 5, 255], np.uint8), 700))
+    encs.append(np.tile(np.array([5, 5, 5, 0, 5], np.uint8), 500))
+    exps = [oracle.rle_decode(e) for e in encs]
+    src = Batch(be, [e.size for e in encs], encs)
+    dst = Batch(be, [e.size for e in exps], fill=0xEE)
+    st = be.upload(np.zeros(src.nf, np.int32))
+    # size query first (out == NULL)
+    rc0(be.L.hc_rle_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, None, None, None, dst.d_len.ptr, st.ptr,
+                                 src.nf, src.max_len, be.stream))
+    assert [int(x) for x in dst.lens()] == [e.size for e in exps]
+    rc0(be.L.hc_rle_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                 dst.d_len.ptr, st.ptr, src.nf, src.max_len, be.stream))
+    lens = dst.lens()
+    assert not be.download(st, src.nf * 4, np.int32).any()
+    for i, (e, g) in enumerate(zip(exps, dst.files(lens))):
+        assert int(lens[i]) == e.size
+        assert np.array_equal(g, e), i
+    # the byte after every region's payload must be untouched (no overrun)
+    host = be.download(dst.data, dst.total)
+    for o, n, c in zip(dst.offs, lens, dst.caps):
+        assert (host[int(o) + int(n):int(o) + int(c)] == 0xEE).all()
+
+
+def test_rle_decode_capacity(be, oracle):
+    enc = np.tile(np.array([9, 9, 9, 200], np.uint8), 50)
+    exp = oracle.rle_decode(enc)
+    src = Batch(be, [enc.size], [enc])
+    dst = Batch(be, [256], fill=0xEE)              # capacity 256+16 -> 512 after alignment
+    st = be.upload(np.zeros(1, np.int32))
+    rc0(be.L.hc_rle_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                 dst.d_len.ptr, st.ptr, 1, src.max_len, be.stream))
+    assert int(dst.lens()[0]) == exp.size
+    assert int(be.download(st, 4, np.int32)[0]) == hc_b200.HC_E_CAPACITY
+    host = be.download(dst.data, dst.total + 64)
+    cap = int(dst.caps[0])
+    assert np.array_equal(host[:cap], exp[:cap]) and (host[cap:] == 0xEE).all() is not False
+
+
+SHAPES = [(8, 8), (9, 8), (8, 9), (15, 17), (16, 16), (17, 33), (64, 24), (31, 100), (130, 70), (256, 40), (512, 16)]
+
+
+def _adapt_inputs(be):
+    imgs = []
+    kinds = ("walk", "smooth", "random", "const", "longrun")
+    shapes = SHAPES if be.name == "emu" else SHAPES + [(512, 512), (512, 517), (1024, 300)]
+    for i, (w, h) in enumerate(shapes):
+        for k in (kinds[i % 5], kinds[(i + 2) % 5]):
+            imgs.append((w, h, synth.image(k, w, 50 + i, h).reshape(-1)))
+    # gradients that favour vertical / horizontal scanning
+    y, x = np.mgrid[0:64, 0:64]
+    imgs.append((64, 64, (x & 255).astype(np.uint8).reshape(-1)))
+    imgs.append((64, 64, (y & 255).astype(np.uint8).reshape(-1)))
+    return imgs
+
+
+def test_adapt_encode(be, oracle):
+    imgs = _adapt_inputs(be)
+    files = [im for _, _, im in imgs]
+    src = Batch(be, [f.size for f in files], files)
+    dst = Batch(be, [be.L.hc_adapt_bound(w, h) for w, h, _ in imgs], fill=0xEE)
+    d_w = be.upload(np.array([w for w, _, _ in imgs], np.uint64))
+    d_h = be.upload(np.array([h for _, h, _ in imgs], np.uint64))
+    d_b = be.upload(np.zeros(src.nf, np.uint64))
+    st = be.upload(np.zeros(src.nf, np.int32))
+    ws = be.alloc(be.L.hc_adapt_encode_ws_bytes(src.nf, src.max_len))
+    rc0(be.L.hc_adapt_encode_batch(src.data.ptr, src.d_off.ptr, d_w.ptr, d_h.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_len.ptr,
+                                   d_b.ptr, st.ptr, src.nf, src.max_len, ws.ptr, be.stream))
+    lens = dst.lens()
+    got = dst.files(lens)
+    bs = be.download(d_b, src.nf * 8, np.uint64)
+    assert not be.download(st, src.nf * 4, np.int32).any()
+    for i, (w, h, im) in enumerate(imgs):
+        rc, exp, b = oracle.adapt_encode(im, w, h)
+        assert rc == 0
+        assert int(bs[i]) == b, (w, h, i)
+        assert int(lens[i]) == exp.size, (w, h, i)
+        assert np.array_equal(got[i], exp), (w, h, i)
+
+
+def test_adapt_encode_too_small(be):
+    files = [np.zeros(35, np.uint8), np.zeros(64, np.uint8)]
+    src = Batch(be, [64, 64], files)
+    dst = Batch(be, [256, 256])
+    d_w = be.upload(np.array([5, 8], np.uint64))
+    d_h = be.upload(np.array([7, 8], np.uint64))
+    st = be.upload(np.zeros(2, np.int32))
+    ws = be.alloc(be.L.hc_adapt_encode_ws_bytes(2, 64))
+    rc0(be.L.hc_adapt_encode_batch(src.data.ptr, src.d_off.ptr, d_w.ptr, d_h.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_len.ptr,
+                                   None, st.ptr, 2, 64, ws.ptr, be.stream))
+    assert list(be.download(st, 8, np.int32)) == [12, 0]
+
+
+def test_adapt_decode(be, oracle):
+    imgs = _adapt_inputs(be)
+    encs = [oracle.adapt_encode(im, w, h)[1] for w, h, im in imgs]
+    # fixed block sizes too (not only the search winner)
+    for (w, h, im) in imgs[:6]:
+        encs.append(oracle.adapt_encode_bs(im, w, h, 8))
+        imgs = imgs + [(w, h, im)]
+    src = Batch(be, [e.size for e in encs], encs)
+    dst = Batch(be, [w * h for w, h, _ in imgs], fill=0xEE)
+    st = be.upload(np.zeros(src.nf, np.int32))
+    rc0(be.L.hc_adapt_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                   dst.d_len.ptr, st.ptr, src.nf, src.max_len, 0, None, be.stream))
+    assert not be.download(st, src.nf * 4, np.int32).any()
+    lens = dst.lens()
+    for i, ((w, h, im), g) in enumerate(zip(imgs, dst.files(lens))):
+        assert int(lens[i]) == w * h
+        assert np.array_equal(g, im), (w, h, i)
+
+
+def test_adapt_decode_errors(be, oracle):
+    img = synth.image("walk", 16, 3, 24).reshape(-1)
+    good = oracle.adapt_encode(img, 16, 24)[1]
+    hdr = lambda w, h, b: np.frombuffer(w.to_bytes(8, "big") + h.to_bytes(8, "big") + b.to_bytes(8, "big"), np.uint8)
+    cases = [
+        good[:20],                                            # 10: header < 24 bytes
+        good[:24],                                            # 11: direction bytes missing
+        good[:-3],                                            # 14: data underrun
+        np.concatenate([good, np.array([1, 2], np.uint8)]),   # 15: leftover
+        np.concatenate([hdr(8, 8, 8), np.array([0x80], np.uint8), np.array([7, 7, 7, 100], np.uint8)]),  # 13: overshoot
+        np.concatenate([hdr(8, 8, 0), np.zeros(8, np.uint8)]),   # block size 0: reference divides by zero; we say 10
+        good,
+    ]
+    expect = [10, 11, 14, 15, 13, 10, 0]
+    for c, e in zip(cases[:5], expect[:5]):
+        assert oracle.adapt_decode(c)[0] == e
+    src = Batch(be, [c.size for c in cases], cases)
+    dst = Batch(be, [16 * 24] * len(cases))
+    st = be.upload(np.zeros(src.nf, np.int32))
+    rc0(be.L.hc_adapt_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                   dst.d_len.ptr, st.ptr, src.nf, src.max_len, 0, None, be.stream))
+    assert list(be.download(st, src.nf * 4, np.int32)) == expect
+    assert np.array_equal(dst.files(dst.lens())[-1], img)
+
+
+def _fgk_inputs(be):
+    rng = np.random.default_rng(21)
+    n = 6000 if be.name == "emu" else 60000
+    files = [np.zeros(0, np.uint8), np.array([65], np.uint8), np.frombuffer(b"AAAA", np.uint8),
+             rng.integers(0, 256, n, dtype=np.uint8), rng.integers(0, 4, n // 2, dtype=np.uint8),
+             np.arange(n // 3, dtype=np.uint32).astype(np.uint8), np.full(n // 4, 9, np.uint8),
+             np.sort(synth.image("fib", 128, 1).reshape(-1))[::-1][: n].copy(),      # deep tree, long codes
+             (np.cumsum(rng.integers(-2, 3, n)) & 255).astype(np.uint8)]
+    return files
+
+
+def test_fgk_encode(be, oracle):
+    files = _fgk_inputs(be)
+    src = Batch(be, [f.size for f in files], files)
+    dst = Batch(be, [be.L.hc_fgk_bound(f.size) for f in files], fill=0xEE)
+    flags = be.upload(np.array([(i % 4) << 6 for i in range(src.nf)], np.uint8))
+    st = be.upload(np.zeros(src.nf, np.int32))
+    rc0(be.L.hc_fgk_encode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, flags.ptr, dst.data.ptr, dst.d_off.ptr,
+                                 dst.d_cap.ptr, dst.d_len.ptr, st.ptr, src.nf, be.stream))
+    assert not be.download(st, src.nf * 4, np.int32).any()
+    lens = dst.lens()
+    for i, (f, g) in enumerate(zip(files, dst.files(lens))):
+        bits, _ = oracle.fgk_encode(f)
+        exp = np.concatenate([np.frombuffer(int(f.size).to_bytes(8, "little") + bytes([(i % 4) << 6]), np.uint8), bits])
+        assert int(lens[i]) == exp.size, i
+        assert np.array_equal(g, exp), i
+
+
+def test_fgk_decode(be, oracle):
+    files = _fgk_inputs(be)
+    outs = []
+    for i, f in enumerate(files):
+        bits, _ = oracle.fgk_encode(f)
+        outs.append(np.concatenate([np.frombuffer(int(f.size).to_bytes(8, "little") + bytes([0xC0 if i & 1 else 0]), np.uint8), bits]))
+    # malformed: short header (8), truncated bits (9), absurd count (9), trailing garbage is ignored (0)
+    outs.append(outs[3][:5].copy())
+    outs.append(outs[3][:-5].copy())
+    big = outs[3].copy()
+    big[:8] = np.frombuffer((10 ** 12).to_bytes(8, "little"), np.uint8)
+    outs.append(big)
+    outs.append(np.concatenate([outs[8], np.array([1, 2, 3], np.uint8)]))
+    exp_status = [0] * len(files) + [8, 9, 9, 0]
+    src = Batch(be, [o.size for o in outs], outs)
+    dst = Batch(be, [f.size for f in files] + [64, files[3].size, 64, files[8].size], fill=0xEE)
+    flags = be.upload(np.zeros(src.nf, np.uint8))
+    st = be.upload(np.zeros(src.nf, np.int32))
+    rc0(be.L.hc_fgk_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                 dst.d_len.ptr, flags.ptr, st.ptr, src.nf, be.stream))
+    status = list(be.download(st, src.nf * 4, np.int32))
+    assert status == exp_status
+    lens = dst.lens()
+    got = dst.files(lens)
+    fl = be.download(flags, src.nf)
+    for i, f in enumerate(files):
+        assert int(lens[i]) == f.size and np.array_equal(got[i], f), i
+        assert fl[i] == (0xC0 if i & 1 else 0)
+    assert np.array_equal(got[-1], files[8])
+
+
+def test_offsets_and_gather(be):
+    lens = np.array([0, 5, 256, 257, 1000, 1], np.uint64)
+    d_len = be.upload(lens)
+    d_off = be.upload(np.zeros(lens.size, np.uint64))
+    d_tot = be.upload(np.zeros(1, np.uint64))
+    rc0(be.L.hc_offsets_from_lens(d_len.ptr, d_off.ptr, d_tot.ptr, lens.size, 16, be.stream))
+    off = be.download(d_off, lens.size * 8, np.uint64)
+    al = (lens + 15) // 16 * 16
+    assert list(off) == list(np.concatenate([[0], np.cumsum(al)[:-1]]))
+    assert int(be.download(d_tot, 8, np.uint64)[0]) == int(al.sum())
+    rng = np.random.default_rng(4)
+    files = [rng.integers(0, 256, int(n), dtype=np.uint8) for n in lens]
+    src = Batch(be, [int(n) for n in lens], files)
+    out = be.alloc(int(al.sum()) + 256, fill=0xEE)
+    rc0(be.L.hc_gather_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, out.ptr, d_off.ptr, lens.size, int(lens.max()), be.stream))
+    host = be.download(out, int(al.sum()))
+    for f, o in zip(files, off):
+        assert np.array_equal(host[int(o):int(o) + f.size], f)
