@@ -17,6 +17,7 @@
 // DECODE: block boundaries depend on the decoded data itself (fresh RLE state per block,
 // a block ends when bw*bh bytes exist), so v1 walks each file's token stream with one thread.
 #pragma once
+#include "rle.cuh"
 #include "runsum.cuh"
 #include "scan.cuh"
 
@@ -317,15 +318,215 @@ adapt_emit_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
 }
 
 // ------------------------------------------------------------------------------------------
-// decode: one thread per file walks the token stream (block starts are data dependent)
+// decode.  Block boundaries depend on the decoded data itself (fresh RLE state per block, a
+// block ends when bw*bh bytes exist), so decoding is split in two:
+//   adapt_index_kernel   one warp per file walks the token stream 32 tokens per step (decoder
+//                        state maps and token lengths by warp scans, as in rle.cuh) and records
+//                        where every block starts; validates the stream (status 10..15).
+//   adapt_expand_kernel  a group of lanes per block decodes its tokens (state-map scan, length
+//                        scan, then expansion) and scatters the bytes in the block's direction.
+// adapt_decode_kernel (one thread per file) remains as the fallback for headers whose block
+// count exceeds the index table (block sizes < 8, which the reference encoder never emits).
+// ------------------------------------------------------------------------------------------
+struct AdaptHeader { u64 w, h, b, nb, dir_bytes, total; i32 status; };
+
+// src/headers.cpp:65-105 + the allocation of src/transform.cpp:340
+HC_DEV AdaptHeader ad_parse_header(const u8 *src, u64 m)
+{
+    AdaptHeader hd;
+    hd.w = hd.h = hd.b = hd.nb = hd.dir_bytes = hd.total = 0;
+    hd.status = 0;
+    if (m < 24) { hd.status = 10; return hd; }            // src/headers.cpp:67-71
+    for (int i = 0; i < 8; i++) hd.w = (hd.w << 8) | src[i];
+    for (int i = 0; i < 8; i++) hd.h = (hd.h << 8) | src[8 + i];
+    for (int i = 0; i < 8; i++) hd.b = (hd.b << 8) | src[16 + i];
+    if (hd.b == 0) { hd.status = 10; return hd; }         // reference: division by zero (UB)
+    const u64 nbx = hd.w / hd.b + (hd.w % hd.b != 0), nby = hd.h / hd.b + (hd.h % hd.b != 0);
+    // direction bytes are read lazily by the reference; missing ones -> 11 (src/headers.cpp:94-98)
+    const u64 avail_bits = (m - 24) * 8;
+    if ((nbx != 0 && nby != 0) && (nbx > avail_bits || nby > avail_bits || nbx * nby > avail_bits)) {
+        hd.status = 11;
+        return hd;
+    }
+    hd.nb = nbx * nby;
+    hd.dir_bytes = (hd.nb + 7) / 8;
+    if (hd.h != 0 && hd.w > ~0ull / hd.h) { hd.status = 100; return hd; }
+    hd.total = hd.w * hd.h;
+    return hd;
+}
+
+constexpr i32 AD_ST_SERIAL = 102;   // internal: block table too small, use the serial decoder
+
+HC_KERNEL HC_LAUNCH_BOUNDS(32, 1)
+adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
+                   const u64 *HC_RESTRICT out_cap, bool have_out, u32 *HC_RESTRICT blk_start, u64 blk_stride,
+                   u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
+{
+    const u32 f = blockIdx.x, lane = threadIdx.x & 31u;
+    if (f >= nf) return;
+    const u64 m = in_len[f];
+    const u8 *src = in + in_off[f];
+    const AdaptHeader hd = ad_parse_header(src, m);
+    if (hd.status) { if (lane == 0) { out_len[f] = 0; status[f] = hd.status; } return; }
+    if (!have_out) { if (lane == 0) { out_len[f] = hd.total; status[f] = 0; } return; }
+    if (hd.total > out_cap[f]) { if (lane == 0) { out_len[f] = hd.total; status[f] = 100; } return; }
+    if (hd.nb + 1 > blk_stride || m > 0xfffffff0ull) { if (lane == 0) { out_len[f] = hd.total; status[f] = AD_ST_SERIAL; } return; }
+    u32 *tab = blk_start + (u64)f * blk_stride;
+    u64 pos = 24 + hd.dir_bytes;
+    i32 err = 0;
+    u64 blk = 0;
+    for (u64 by = 0; by < hd.h && !err; by += hd.b) {
+        const u64 bh = by + hd.b > hd.h ? hd.h - by : hd.b;
+        for (u64 bx = 0; bx < hd.w && !err; bx += hd.b, blk++) {
+            const u64 bw = bx + hd.b > hd.w ? hd.w - bx : hd.b;
+            const u64 req = bw * bh;
+            if (lane == 0) tab[blk] = (u32)pos;
+            u64 produced = 0;
+            u32 state = 0, prev_last = 0;
+            while (produced < req) {
+                const u64 idx = pos + lane;
+                const bool valid = idx < m;
+                const u32 b = valid ? src[idx] : 0u;
+                u32 pb = shfl_up(b, 1);
+                if (lane == 0) pb = prev_last;
+                u32 map = !valid ? MAP_ID : (b == pb ? MAP_EQ : MAP_NE);
+                u32 inc = map;
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 t = shfl_up(inc, d);
+                    if (lane >= (u32)d) inc = map_compose(t, inc);
+                }
+                u32 exm = shfl_up(inc, 1);
+                if (lane == 0) exm = MAP_ID;
+                const u32 st_before = map_apply(exm, state);
+                u32 len = !valid ? 0u : (st_before == 3u ? b : 1u);
+                u32 cum = len;
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 t = shfl_up(cum, d);
+                    if (lane >= (u32)d) cum += t;
+                }
+                const u64 rem = req - produced;
+                const u32 vmask = ballot(valid);
+                const u32 hit = ballot(valid && (u64)cum >= rem);
+                if (hit == 0u) {
+                    const u32 nvalid = (u32)popc(vmask);
+                    if (nvalid == 0u) { err = 14; break; }              // src/transform.cpp:170-174
+                    produced += shfl(cum, (int)nvalid - 1);
+                    state = map_apply(shfl(inc, (int)nvalid - 1), state);
+                    prev_last = shfl(b, (int)nvalid - 1);
+                    pos += nvalid;
+                    if (nvalid < 32u && produced < req) { err = 14; break; }
+                } else {
+                    const int e = ffs(hit) - 1;
+                    if ((u64)shfl(cum, e) > rem) { err = 13; break; }   // src/transform.cpp:180-184
+                    pos += (u32)e + 1u;
+                    produced = req;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        tab[hd.nb] = (u32)pos;
+        out_len[f] = hd.total;
+        status[f] = err ? err : (pos != m ? 15 : 0);                    // src/transform.cpp:354-358
+    }
+}
+
+constexpr int AD_EXP_TPB = 256;
+
+HC_KERNEL HC_LAUNCH_BOUNDS(AD_EXP_TPB, 4)
+adapt_expand_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
+                    const u32 *HC_RESTRICT blk_start, u64 blk_stride, u8 *HC_RESTRICT out,
+                    const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, u32 nf)
+{
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
+        if (status[f] != 0) continue;
+        const u8 *src = in + in_off[f];
+        const AdaptHeader hd = ad_parse_header(src, in_len[f]);
+        if (hd.nb == 0) continue;
+        const u32 *tab = blk_start + (u64)f * blk_stride;
+        u8 *mat = out + out_off[f];
+        const u32 L = ad_lanes(hd.b), G = 32u / L, gl = lane % L, gi = lane / L;
+        const u64 ngroups = (hd.nb + G - 1) / G;
+        const u64 stride = (u64)gridDim.x * (AD_EXP_TPB / 32);
+        for (u64 grp = (u64)blockIdx.x * (AD_EXP_TPB / 32) + wid; grp < ngroups; grp += stride) {
+            const u64 blk = grp * G + gi;
+            const bool live = blk < hd.nb;
+            const BlockGeom g = ad_geom(hd.w, hd.h, hd.b, live ? blk : 0);
+            const u32 t0 = live ? tab[blk] : 0u, t1 = live ? tab[blk + 1] : 0u;
+            const u32 ntok = t1 - t0, per = (ntok + L - 1) / L;
+            u32 lo = t0 + gl * per, hi = lo + per;
+            if (lo > t1) lo = t1;
+            if (hi > t1) hi = t1;
+            const bool hor = live ? ((src[24 + (blk >> 3)] >> (7 - (blk & 7))) & 1u) : true;
+            // pass A: decoder state map of this lane's token chunk
+            u32 map = MAP_ID;
+            {
+                u32 prev = lo > t0 ? src[lo - 1] : 0x100u;
+                for (u32 i = lo; i < hi; i++) {
+                    u32 b = src[i];
+                    map = map_compose(map, b == prev ? MAP_EQ : MAP_NE);
+                    prev = b;
+                }
+            }
+            u32 inc = map;
+            for (u32 d = 1; d < L; d <<= 1) {
+                u32 t = shfl_up(inc, d);
+                if (gl >= d) inc = map_compose(t, inc);
+            }
+            u32 exm = shfl_up(inc, 1);
+            if (gl == 0) exm = MAP_ID;
+            const u32 st_in = map_apply(exm, 0u);                       // fresh state per block
+            // pass B: output bytes produced by the chunk
+            u32 cnt = 0;
+            {
+                u32 s = st_in, prev = lo > t0 ? src[lo - 1] : 0x100u;
+                for (u32 i = lo; i < hi; i++) {
+                    u32 b = src[i];
+                    if (s == 3u) { cnt += b; s = 0; }
+                    else { cnt += 1u; s = (s == 0u) ? 1u : (b == prev ? s + 1u : 1u); }
+                    prev = b;
+                }
+            }
+            u32 cum = cnt;
+            for (u32 d = 1; d < L; d <<= 1) {
+                u32 t = shfl_up(cum, d);
+                if (gl >= d) cum += t;
+            }
+            // pass C: expand and scatter
+            if (lo < hi) {
+                const u32 req = g.bw * g.bh, inner = hor ? g.bw : g.bh;
+                u32 o = cum - cnt;
+                u32 co = o / inner, ci = o % inner;
+                u8 *bp = mat + g.base;
+                u32 s = st_in, prev = lo > t0 ? src[lo - 1] : 0u;
+                for (u32 i = lo; i < hi; i++) {
+                    u32 b = src[i], len, val;
+                    if (s == 3u) { len = b; val = prev; s = 0; }
+                    else { len = 1; val = b; s = (s == 0u) ? 1u : (b == prev ? s + 1u : 1u); }
+                    prev = b;
+                    for (u32 j = 0; j < len && o < req; j++, o++) {
+                        u64 a = hor ? (u64)co * hd.w + ci : (u64)ci * hd.w + co;
+                        bp[a] = (u8)val;
+                        if (++ci == inner) { ci = 0; co++; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// serial fallback: one thread per file walks the token stream
 // ------------------------------------------------------------------------------------------
 HC_KERNEL HC_LAUNCH_BOUNDS(32, 1)
 adapt_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                     u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
-                    u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
+                    u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf, i32 only_status)
 {
     const u32 f = blockIdx.x;
     if (f >= nf || threadIdx.x != 0) return;
+    if (only_status >= 0 && status[f] != only_status) return;   // fallback pass: selected files only
     const u64 m = in_len[f];
     const u8 *src = in + in_off[f];
     out_len[f] = 0;

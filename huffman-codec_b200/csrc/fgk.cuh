@@ -4,15 +4,24 @@
 // header src/headers.cpp:107-125 and bit packing src/main.cpp:78-84.
 //
 // The tree update is serial inside one stream, so the parallelism is the batch: ONE WARP PER
-// FILE, tree in shared memory (4.8 KB per stream), all 32 lanes executing the same control flow.
-// The reference's pointer tree with its whole-tree recursive leader search is replaced by the
-// node-number indexed form (slot = node number 0..512, siblings adjacent, even slot = left
-// child = bit 0; weights are non-decreasing in slot order), see SURVEY.md A.5:
-//   code(s)   : collect s&1 while s = parent[s] until the root (slot 512)
-//   leader(s) : last slot l >= s with w[l] == w[s]  -- 32 slots per step with one warp ballot
-//   swap      : exchange the contents (kid/symbol) of slots s and l, re-point their children
-// Encoding walks leaf -> root once, collecting the code bits and updating weights in the same
-// pass until the first swap (after which the old path is finished by a pure parent chase).
+// FILE with the tree in shared memory (6.7 KB per stream).  All 32 lanes execute the same control
+// flow and only READ the tree; lane 0 is the only writer.  The kernel is instruction-issue bound
+// (about 7 resident streams per warp scheduler at 4096 files), so the layout is chosen to make
+// the per-level work of the leaf->root walk as few instructions as possible:
+//
+//   slot = node number 0..512: siblings adjacent, even slot = left child = bit 0,
+//   weights non-decreasing in slot order, so the block leader of s is the last slot l >= s with
+//   w[l] == w[s].
+//   up[s]   = { weight, SHARED-MEMORY ADDRESS of up[parent(s)] }   one LDS.64, no address math
+//   down[s] = internal: shared address of down[left child]; leaf: (symbol << 1) | 1
+//   The code bit of slot s is bit 3 of the address of up[s] (8-byte entries, 16-byte aligned base).
+//
+//   per level: LDS.64 up[s], LDS.32 up[s+1].w -> if the weights differ (common case) there is no
+//   leader to find: lane 0 stores w+1 and the walk follows the parent address.  Only when they are
+//   equal the warp probes 32 slots per ballot for the leader and, if needed, swaps the two subtrees.
+//   Encoding collects the code bits on the same walk (shifted in from the top, a marker bit
+//   tracks the length) until the first swap, after which the old path is finished separately.
+//
 // Bits are packed MSB-first into 32-bit words; each lane keeps one word and the warp flushes
 // 128 bytes at a time (coalesced).  The 9-byte container header goes through the same writer.
 #pragma once
@@ -20,102 +29,187 @@
 
 namespace hcd {
 
-constexpr int FGK_WARPS = 4;            // streams per CTA
-constexpr int FGK_ROOT = 512;
-constexpr int FGK_WPAD = 548;           // w[] padded with sentinels for the 32-wide leader probe
-constexpr i16 FGK_NYT = -257;           // kid[] < 0: leaf, symbol = -1 - kid; FGK_NYT: the NYT leaf
+constexpr int FGK_WARPS = 4;             // streams per CTA
+constexpr u32 FGK_ROOT = 512;
+constexpr u32 FGK_NSLOT = 514;           // slots 0..512 + one sentinel (weight 0xffffffff)
+constexpr u32 FGK_LEAF_NYT = (256u << 1) | 1u;
 
-struct FgkTree {
-    u32 w[FGK_WPAD];
-    u16 parent[FGK_ROOT + 2];
-    i16 kid[FGK_ROOT + 2];
-    u16 slot_of[256];
-    u32 nyt;
+struct HC_ALIGNED16 FgkTree {
+    uint2 up[FGK_NSLOT];     // {weight, shared address of the parent's up entry}
+    u32 down[FGK_NSLOT];     // see above
+    u16 slot_of[256];        // leaf slot of a symbol, 0xffff = not yet transmitted
+    u8 buf[128];             // staging of 128 symbols (one coalesced transfer)
+    u8 pad[8];
 };
 
-HC_DEV void fgk_init(FgkTree &t, u32 lane)
-{
-    for (u32 i = lane; i < (u32)FGK_WPAD; i += 32) t.w[i] = i <= (u32)FGK_ROOT ? 0u : 0xffffffffu;
-    for (u32 i = lane; i < 256u; i += 32) t.slot_of[i] = 0xffffu;
-    for (u32 i = lane; i < (u32)FGK_ROOT + 2u; i += 32) { t.kid[i] = FGK_NYT; t.parent[i] = (u16)FGK_ROOT; }
-    if (lane == 0) t.nyt = FGK_ROOT;
-    syncwarp();
-}
+struct FgkCtx {              // shared addresses, identical in every lane
+    u32 up, down, slot_of, buf, root, sentinel, nyt;
+};
 
-// NYT split (src/huffman.cpp:99-111): returns the slot of the new symbol leaf.
-// Only lane 0 writes the tree; the warp barrier publishes the writes to the other lanes.
-HC_DEV u32 fgk_split(FgkTree &t, u32 sym, u32 lane)
+HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
 {
-    const u32 n = t.nyt;
-    syncwarp();                               // every lane has read nyt before it moves
+    c.up = smem_addr(&t.up[0]);
+    c.down = smem_addr(&t.down[0]);
+    c.slot_of = smem_addr(&t.slot_of[0]);
+    c.buf = smem_addr(&t.buf[0]);
+    c.root = c.up + 8u * FGK_ROOT;
+    c.sentinel = c.up + 8u * (FGK_ROOT + 1u);
+    c.nyt = c.root;
+    for (u32 i = lane; i < 128u; i += 32) sts32(c.slot_of + 4u * i, 0xffffffffu);
     if (lane == 0) {
-        t.kid[n] = (i16)(n - 2);
-        t.parent[n - 2] = (u16)n;
-        t.parent[n - 1] = (u16)n;
-        t.kid[n - 1] = (i16)(-1 - (i32)sym);
-        t.kid[n - 2] = FGK_NYT;
-        t.w[n - 1] = 0;
-        t.w[n - 2] = 0;
-        t.slot_of[sym] = (u16)(n - 1);
-        t.nyt = n - 2;
+        uint2 z; z.x = 0; z.y = 0;
+        sts64(c.root, z);
+        z.x = 0xffffffffu;
+        sts64(c.sentinel, z);
+        sts32(c.down + 4u * FGK_ROOT, FGK_LEAF_NYT);
     }
     syncwarp();
-    return n - 1;
 }
 
-// FGK update from slot s (src/huffman.cpp:113-127).  If `coding`, also collects the code of s
-// (pre-update tree) into code/depth: bit d of `code` = bit emitted (depth-d)th, i.e. the value
-// `code` printed MSB-first over `depth` bits is the root->leaf path.
-template <bool CODING>
-HC_DEV void fgk_update(FgkTree &t, u32 s, u32 lane, u64 &code, u32 &depth)
+HC_DEV u32 fgk_down_of(const FgkCtx &c, u32 a) { return c.down + ((a - c.up) >> 1); }   // up address -> down address
+HC_DEV u32 fgk_up_of(const FgkCtx &c, u32 d) { return c.up + ((d - c.down) << 1); }
+
+// NYT split (src/huffman.cpp:99-111): the NYT slot n becomes internal with children n-2 (new NYT)
+// and n-1 (leaf of `sym`).  Returns the up address of the new leaf.
+HC_DEV u32 fgk_split(FgkCtx &c, u32 sym, u32 lane)
 {
-    // All lanes walk the same path (uniform control flow) and only READ the tree; lane 0 is the
-    // only writer.  Nothing written at one level is read again at a higher level of the same
-    // walk (parents, leaders and probes all have larger slot numbers), so one warp barrier at
-    // the end is enough to publish the update before the next symbol.
-    bool coding = CODING;
-    while (s != (u32)FGK_ROOT) {
-        const u32 ws = t.w[s];
-        const u32 wn = t.w[s + 1 + lane];
-        u32 p = t.parent[s];
-        if (coding) {
-            code |= (u64)(s & 1u) << (depth & 63u);
-            depth++;
-        }
-        u32 m = ~ballot(wn == ws);
-        u32 run = m ? (u32)ffs(m) - 1u : 32u;
-        u32 l = s + run;
-        while (run == 32u) {               // block longer than the probe: keep scanning
-            m = ~ballot(t.w[l + 1 + lane] == ws);
-            run = m ? (u32)ffs(m) - 1u : 32u;
-            l += run;
-        }
-        if (l != s && l != p) {
-            if (coding) {                  // finish the code on the old path
-                for (u32 c = p; c != (u32)FGK_ROOT; c = t.parent[c]) {
-                    code |= (u64)(c & 1u) << (depth & 63u);
-                    depth++;
-                }
-                coding = false;
-            }
-            if (lane == 0) {
-                const i16 ks = t.kid[s], kl = t.kid[l];
-                t.kid[s] = kl;
-                t.kid[l] = ks;
-                if (kl >= 0) { t.parent[kl] = (u16)s; t.parent[kl + 1] = (u16)s; }
-                else if (kl == FGK_NYT) t.nyt = s;
-                else t.slot_of[-1 - kl] = (u16)s;
-                if (ks >= 0) { t.parent[ks] = (u16)l; t.parent[ks + 1] = (u16)l; }
-                else if (ks == FGK_NYT) t.nyt = l;
-                else t.slot_of[-1 - ks] = (u16)l;
-            }
-            s = l;
-            p = t.parent[l];
-        }
-        if (lane == 0) t.w[s] = ws + 1u;
-        s = p;
+    const u32 n = c.nyt;                      // up address of the current NYT
+    syncwarp();                               // every lane has done its slot_of / nyt-path reads
+    if (lane == 0) {
+        uint2 z; z.x = 0; z.y = n;
+        sts64(n - 8u, z);                     // leaf  (slot n-1): weight 0, parent n
+        sts64(n - 16u, z);                    // NYT   (slot n-2)
+        const u32 dn = fgk_down_of(c, n);
+        sts32(dn, dn - 8u);                   // internal: address of the left child's down entry
+        sts32(dn - 4u, (sym << 1) | 1u);
+        sts32(dn - 8u, FGK_LEAF_NYT);
+        sts16(c.slot_of + 2u * sym, ((n - c.up) >> 3) - 1u);
     }
-    if (lane == 0) t.w[FGK_ROOT]++;
+    c.nyt = n - 16u;
+    syncwarp();
+    return n - 8u;
+}
+
+// collect one code bit (bit 3 of the up address) at the top of the 64-bit accumulator hi:lo
+HC_DEV void fgk_code_bit(u32 a, u32 &hi, u32 &lo)
+{
+    lo = funnel_r(lo, hi, 1);
+    hi = (hi >> 1) | ((a << 28) & 0x80000000u);
+}
+
+// Ordering of lane 0's weight store against the other lanes' reads of the same level.  On the
+// GPU a converged warp executes the predicated store after the (earlier) load instruction of all
+// lanes, so the product build adds nothing; -DHC_FGK_STRICT (and the emulator) insert a warp
+// barrier per level for tools that check the CUDA memory model formally (racecheck).
+#if defined(HC_EMU) || defined(HC_FGK_STRICT)
+#define FGK_LEVEL_SYNC() syncwarp()
+#else
+#define FGK_LEVEL_SYNC() ((void)0)
+#endif
+
+// slow path of one level: w[s+1] == w[s].  Finds the block leader (32 slots per ballot) and swaps
+// the subtrees if required (src/huffman.cpp:115-122).  Returns true if a swap happened; a / parent
+// are updated to the slot the node now occupies.  `watch` is the next symbol to be coded: if its
+// leaf moves, *moved is set so that the caller refreshes its prefetched slot.
+HC_DEV bool fgk_leader_swap(FgkCtx &c, u32 &a, u32 &parent, u32 ws, u32 lane, u32 watch, bool &moved)
+{
+    u32 l = a + 8u;
+    // the common short block: one more plain load decides it without a ballot
+    if (lds32(a + 16u) == ws) {
+        u32 run;
+        l = a;
+        do {
+            u32 pa = l + 8u * (1u + lane);
+            pa = pa < c.sentinel ? pa : c.sentinel;
+            u32 m = ~ballot(lds32(pa) == ws);
+            run = m ? (u32)ffs(m) - 1u : 32u;
+            l += 8u * run;
+        } while (run == 32u);
+    }
+    if (l == parent) return false;
+    // exchange the contents of slots a and l; every lane reads, lane 0 writes
+    const u32 da = fgk_down_of(c, a), dl = fgk_down_of(c, l);
+    const u32 ka = lds32(da), kl = lds32(dl);
+    syncwarp();
+    if (lane == 0) {
+        sts32(da, kl);
+        sts32(dl, ka);
+        if (!(kl & 1u)) { u32 cu = fgk_up_of(c, kl); sts32(cu + 4u, a); sts32(cu + 12u, a); }
+        else if (kl != FGK_LEAF_NYT) sts16(c.slot_of + (kl & ~1u), (a - c.up) >> 3);
+        if (!(ka & 1u)) { u32 cu = fgk_up_of(c, ka); sts32(cu + 4u, l); sts32(cu + 12u, l); }
+        else if (ka != FGK_LEAF_NYT) sts16(c.slot_of + (ka & ~1u), (l - c.up) >> 3);
+    }
+    if (kl == FGK_LEAF_NYT) c.nyt = a;
+    if (ka == FGK_LEAF_NYT) c.nyt = l;
+    const u32 wleaf = (watch << 1) | 1u;
+    if (ka == wleaf || kl == wleaf) moved = true;
+    a = l;
+    parent = lds32(l + 4u);
+    return true;
+}
+
+// FGK update from the node at up address a (src/huffman.cpp:113-127); `count` = symbols processed
+// including this one (= the new root weight).  Nothing written at one level is read again at a
+// higher level of the same walk (parents, leaders and probes all have larger slot numbers); the
+// barrier at the end publishes lane 0's writes before the next symbol.  The parent's entry is
+// fetched one level ahead (software pipelining of the dependent shared-memory loads).
+HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, bool &moved)
+{
+    const bool w0 = lane == 0;
+    if (a != c.root) {
+        uint2 n = lds64(a);
+        u32 w1 = lds32(a + 8u);
+        for (;;) {
+            u32 parent = n.y;
+            uint2 pn = lds64(parent);
+            u32 pw1 = lds32(parent + 8u);
+            if (w1 == n.x && fgk_leader_swap(c, a, parent, n.x, lane, watch, moved)) {
+                pn = lds64(parent);
+                pw1 = lds32(parent + 8u);
+            }
+            FGK_LEVEL_SYNC();
+            sts32_if(w0, a, n.x + 1u);
+            if (parent == c.root) break;
+            a = parent; n = pn; w1 = pw1;
+        }
+    }
+    sts32_if(w0, c.root, count);
+    syncwarp();
+}
+
+// same walk, also collecting the code of the start node in the PRE-update tree
+// (encode precedes update, src/transform.cpp:372-375).  hi:lo must enter as 0x80000000:0.
+// The update path leaves the code path at the first swap; the rest of the old path is then
+// finished by a pure parent chase (safe: the first swap never re-parents an old-path node).
+HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u32 &lo, u32 watch, bool &moved)
+{
+    const bool w0 = lane == 0;
+    uint2 n = lds64(a);                       // a is a leaf: never the root
+    u32 w1 = lds32(a + 8u);
+    for (;;) {
+        u32 parent = n.y;
+        uint2 pn = lds64(parent);
+        u32 pw1 = lds32(parent + 8u);
+        fgk_code_bit(a, hi, lo);
+        if (w1 == n.x) {
+            const u32 old_parent = parent;
+            if (fgk_leader_swap(c, a, parent, n.x, lane, watch, moved)) {
+                if (old_parent != c.root) {   // pn still holds the old parent's entry
+                    fgk_code_bit(old_parent, hi, lo);
+                    for (u32 p = pn.y; p != c.root; p = lds32(p + 4u)) fgk_code_bit(p, hi, lo);
+                }
+                FGK_LEVEL_SYNC();
+                sts32_if(w0, a, n.x + 1u);
+                fgk_update_plain(c, parent, lane, count, watch, moved);
+                return;
+            }
+        }
+        FGK_LEVEL_SYNC();
+        sts32_if(w0, a, n.x + 1u);
+        if (parent == c.root) break;
+        a = parent; n = pn; w1 = pw1;
+    }
+    sts32_if(w0, c.root, count);
     syncwarp();
 }
 
@@ -125,7 +219,7 @@ struct BitWriter {
     u32 nacc;      // valid low bits of acc (< 32 between calls)
     u32 widx;      // words produced so far
     u32 mine;      // this lane's word of the current 32-word group
-    u32 *dst;      // 128-byte aligned
+    u32 *dst;
     u64 cap_words;
     bool overflow;
 };
@@ -138,7 +232,7 @@ HC_DEV void bw_init(BitWriter &b, u8 *dst, u64 cap_bytes)
     b.overflow = false;
 }
 
-HC_DEV void bw_put(BitWriter &b, u32 v, u32 d, u32 lane)   // d <= 32
+HC_DEV void bw_put(BitWriter &b, u32 v, u32 d, u32 lane)   // 0 <= d <= 32, v < 2^d
 {
     b.acc = (b.acc << d) | v;
     b.nacc += d;
@@ -152,6 +246,21 @@ HC_DEV void bw_put(BitWriter &b, u32 v, u32 d, u32 lane)   // d <= 32
             else b.overflow = true;
         }
     }
+}
+
+// emit the code collected in hi:lo (marker scheme of fgk_code_bit); returns false if the code is
+// longer than 56 bits (impossible below 2^32 symbols)
+HC_DEV bool bw_put_code(BitWriter &b, u32 hi, u32 lo, u32 lane)
+{
+    if (lo == 0u) {                                   // depth <= 31: everything is in hi
+        const u32 d = 32u - (u32)ffs(hi);             // marker = lowest set bit of hi
+        if (d) bw_put(b, hi >> (32u - d), d, lane);
+        return true;
+    }
+    const u32 d2 = 32u - (u32)ffs(lo);                // bits of the code that live in lo
+    bw_put(b, hi, 32, lane);
+    if (d2) bw_put(b, lo >> (32u - d2), d2, lane);
+    return d2 <= 24u;
 }
 
 // flush the tail; returns the total number of bytes of the stream
@@ -177,11 +286,12 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
                   const u64 *HC_RESTRICT out_cap, u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
 {
     HC_SHARED FgkTree trees[FGK_WARPS];
+    HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const u32 f = blockIdx.x * FGK_WARPS + wid;
     if (f >= nf) return;
-    FgkTree &t = trees[wid];
-    fgk_init(t, lane);
+    FgkCtx c;
+    fgk_init(c, trees[wid], lane);
 
     const u64 m = sym_len[f];
     const u32 *src = (const u32 *)(sym + sym_off[f]);     // 256-byte aligned region
@@ -192,39 +302,42 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
     bw_put(bw, bswap32((u32)(m >> 32)), 32, lane);
     bw_put(bw, flags ? flags[f] : 0u, 8, lane);
 
-    bool too_long = false;
-    u32 chunk = 0, chunk_next = 0;                        // 4 symbols per lane, 128 per warp
+    bool too_long = m > 0xfffffff0ull;                    // weights are 32-bit
+    u32 chunk = 0;                                        // 4 symbols per lane, 128 per warp
     if (m > 0) chunk = ldg32(src + lane);
+    u32 count = 0;
     for (u64 i0 = 0; i0 < m; i0 += 128) {
-        if (i0 + 128 < m) chunk_next = ldg32(src + (i0 + 128) / 4 + lane);
-        u32 cnt = (m - i0) < 128 ? (u32)(m - i0) : 128u;
+        syncwarp();                                       // every lane is done with the previous buffer
+        sts32(c.buf + 4u * lane, chunk);
+        syncwarp();
+        if (i0 + 128 < m) chunk = ldg32(src + (i0 + 128) / 4 + lane);   // prefetch the next 128 symbols
+        const u32 cnt = (m - i0) < 128 ? (u32)(m - i0) : 128u;
+        u32 y = lds8(c.buf);
+        u32 slot = lds16(c.slot_of + 2u * y);
         for (u32 i = 0; i < cnt; i++) {
-            u32 word = shfl(chunk, (int)(i >> 2));
-            u32 y = (word >> (8u * (i & 3u))) & 0xffu;
-            u32 s = t.slot_of[y];
-            u64 code = 0;
-            u32 depth = 0;
-            if (s == 0xffffu) {
+            // fetch the next symbol and its leaf slot before the update; the update reports if
+            // that leaf moved (swap) or was created (same new symbol twice) so the slot is re-read
+            const u32 yn = lds8(c.buf + ((i + 1u) & 127u));
+            u32 slot_n = lds16(c.slot_of + 2u * yn);
+            bool moved = false;
+            u32 hi = 0x80000000u, lo = 0u;
+            count++;
+            if (slot == 0xffffu) {
                 // not yet transmitted: NYT code followed by the 8 raw bits (src/huffman.cpp:42-51)
-                for (u32 c = t.nyt; c != (u32)FGK_ROOT; c = t.parent[c]) {
-                    code |= (u64)(c & 1u) << (depth & 63u);
-                    depth++;
-                }
-                if (depth > 56u) too_long = true;
-                if (depth > 32u) bw_put(bw, (u32)(code >> 32), depth - 32u, lane);
-                bw_put(bw, (u32)code, depth > 32u ? 32u : depth, lane);
+                for (u32 p = c.nyt; p != c.root; p = lds32(p + 4u)) fgk_code_bit(p, hi, lo);
+                if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
                 bw_put(bw, y, 8, lane);
-                s = fgk_split(t, y, lane);
-                u64 dummy = 0; u32 dd = 0;
-                fgk_update<false>(t, s, lane, dummy, dd);
+                const u32 leaf = fgk_split(c, y, lane);
+                fgk_update_plain(c, leaf, lane, count, yn, moved);
+                if (yn == y) moved = true;
             } else {
-                fgk_update<true>(t, s, lane, code, depth);
-                if (depth > 56u) too_long = true;
-                if (depth > 32u) bw_put(bw, (u32)(code >> 32), depth - 32u, lane);
-                bw_put(bw, (u32)code, depth > 32u ? 32u : depth, lane);
+                fgk_update_coding(c, c.up + 8u * slot, lane, count, hi, lo, yn, moved);
+                if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
             }
+            if (moved) slot_n = lds16(c.slot_of + 2u * yn);
+            y = yn;
+            slot = slot_n;
         }
-        chunk = chunk_next;
     }
     u64 total = bw_finish(bw, lane);
     if (lane == 0) {
@@ -236,12 +349,12 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
 // MSB-first bit reader over 128-byte chunks held one word per lane
 struct BitReader {
     u64 win;        // next bits, MSB aligned
-    u32 wbits;      // valid bits in win
+    u32 wbits;      // valid bits in win (> 32 between calls)
     u32 ridx;       // next word index to pull into the window
     u32 chunk, chunk_next;
     const u32 *src;
-    u64 nwords;     // words that may be loaded (region capacity)
-    u64 avail;      // bits still available in the file (consumed bits are subtracted)
+    u64 nwords;     // words that may be loaded
+    u64 avail;      // bits of the file not yet consumed
 };
 
 HC_DEV void br_refill(BitReader &r, u32 lane)
@@ -261,7 +374,7 @@ HC_DEV void br_refill(BitReader &r, u32 lane)
 HC_DEV void br_init(BitReader &r, const u8 *p, u64 len_bytes, u32 lane)
 {
     r.src = (const u32 *)p;
-    r.nwords = (len_bytes + 3u) / 4u;      // reads stay inside the 256-byte padded region
+    r.nwords = (len_bytes + 3u) / 4u;      // reads stay inside the padded region
     r.avail = len_bytes * 8u;
     r.chunk = lane < r.nwords ? ldg32(r.src + lane) : 0u;
     r.chunk_next = 32u + lane < r.nwords ? ldg32(r.src + 32u + lane) : 0u;
@@ -270,14 +383,19 @@ HC_DEV void br_init(BitReader &r, const u8 *p, u64 len_bytes, u32 lane)
     br_refill(r, lane);
 }
 
-// take d (1..32) bits; caller checks r.avail first
-HC_DEV u32 br_get(BitReader &r, u32 d, u32 lane)
+// drop d (1..32) bits that the caller has already looked at
+HC_DEV void br_skip(BitReader &r, u32 d, u32 lane)
 {
-    u32 v = (u32)(r.win >> (64u - d));
     r.win <<= d;
     r.wbits -= d;
     r.avail -= d;
     if (r.wbits <= 32u) br_refill(r, lane);
+}
+
+HC_DEV u32 br_get(BitReader &r, u32 d, u32 lane)   // 1..32 bits; caller checks r.avail first
+{
+    u32 v = (u32)(r.win >> (64u - d));
+    br_skip(r, d, lane);
     return v;
 }
 
@@ -287,11 +405,12 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                   u64 *HC_RESTRICT sym_len, u8 *HC_RESTRICT flags, i32 *HC_RESTRICT status, u32 nf)
 {
     HC_SHARED FgkTree trees[FGK_WARPS];
+    HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const u32 f = blockIdx.x * FGK_WARPS + wid;
     if (f >= nf) return;
-    FgkTree &t = trees[wid];
-    fgk_init(t, lane);
+    FgkCtx c;
+    fgk_init(c, trees[wid], lane);
 
     const u64 n = in_len[f];
     if (n < 9) {                                         // src/main.cpp:99-104
@@ -306,45 +425,60 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     u32 fl = br_get(br, 8, lane);
     if (lane == 0 && flags) flags[f] = (u8)fl;
     const u64 cap = sym_cap[f];
-    if (m > cap || m > br.avail + 1u) {
-        // more symbols than capacity; (every symbol after the first costs >= 1 bit, so a count
-        // beyond avail+1 is a guaranteed underrun -> the reference exits with 9)
+    if (m > cap || m > br.avail + 1u || m > 0xfffffff0ull) {
+        // every symbol after the first costs >= 1 bit: a count beyond avail+1 is a guaranteed
+        // underrun, for which the reference exits with 9 (src/transform.cpp:394-398)
         if (lane == 0) { sym_len[f] = m; status[f] = (m > br.avail + 1u) ? 9 : 100; }
         return;
     }
     u32 *dst = (u32 *)(sym + sym_off[f]);
-    u32 mine = 0;
+    const u32 root_down = c.down + 4u * FGK_ROOT;
     i32 err = 0;
-    u64 i = 0;
-    for (; i < m; i++) {
-        u32 s = FGK_ROOT;
-        i32 k = t.kid[s];
-        while (k >= 0) {
-            if (br.avail < 1u) { err = 9; break; }
-            s = (u32)k + br_get(br, 1, lane);
-            k = t.kid[s];
+    u32 count = 0;
+    for (u64 i = 0; i < m; i++) {
+        // walk down on a private copy of the window's top 32 bits, consume them afterwards
+        u32 d = root_down, k = lds32(d), t = (u32)(br.win >> 32), len = 0;
+        while (!(k & 1u)) {
+            if (len == 32u) {                            // code longer than 32 bits (very deep tree)
+                if (br.avail < 32u) { err = 9; break; }
+                br_skip(br, 32, lane);
+                t = (u32)(br.win >> 32);
+                len = 0;
+            }
+            d = k + ((t >> 31) << 2);
+            t <<= 1;
+            len++;
+            k = lds32(d);
         }
         if (err) break;
-        u32 y;
-        if (k == FGK_NYT) {
+        if (len) {
+            if (br.avail < len) { err = 9; break; }      // ran out of bits inside a code
+            br_skip(br, len, lane);
+        }
+        u32 y, a;
+        if (k == FGK_LEAF_NYT) {
             if (br.avail < 8u) { err = 9; break; }
             y = br_get(br, 8, lane);
             // a raw symbol that is already in the tree is still decoded as that symbol
-            // (src/huffman.cpp:74-86); update then starts from its existing leaf
-            u32 ex = t.slot_of[y];
-            s = ex == 0xffffu ? fgk_split(t, y, lane) : ex;
+            // (src/huffman.cpp:74-86); the update then starts from its existing leaf
+            const u32 ex = lds16(c.slot_of + 2u * y);
+            a = ex == 0xffffu ? fgk_split(c, y, lane) : c.up + 8u * ex;
         } else {
-            y = (u32)(-1 - k);
+            y = k >> 1;
+            a = fgk_up_of(c, d);
         }
-        u64 dummy = 0; u32 dd = 0;
-        fgk_update<false>(t, s, lane, dummy, dd);
-        u32 li = (u32)(i & 127u);
-        if (lane == (li >> 2)) mine |= y << (8u * (li & 3u));
-        if (li == 127u) { stg32_stream(dst + (i >> 7) * 32u + lane, mine); mine = 0; }
+        count++;
+        if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
+        bool moved = false;
+        fgk_update_plain(c, a, lane, count, 0x1ffu, moved);   // ends with a warp barrier
+        if ((i & 127u) == 127u) {
+            stg32_stream(dst + (i >> 7) * 32u + lane, lds32(c.buf + 4u * lane));
+            syncwarp();
+        }
     }
     if (!err) {
         u32 rem = (u32)(m & 127u);                         // symbols in the last partial group
-        if (rem && lane < (rem + 3u) / 4u) dst[(m >> 7) * 32u + lane] = mine;
+        if (rem && lane < (rem + 3u) / 4u) dst[(m >> 7) * 32u + lane] = lds32(c.buf + 4u * lane);
     }
     if (lane == 0) { sym_len[f] = m; status[f] = err; }
 }

@@ -317,10 +317,11 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
     return 0;
 }
 
+static inline u64 ad_blk_stride(u64 max_out_len) { return max_out_len / 32 + 16; }
+
 extern "C" uint64_t hc_adapt_decode_ws_bytes(uint32_t nf, uint64_t max_out_len)
 {
-    (void)nf; (void)max_out_len;
-    return 256;   // v1 decoder needs no scratch
+    return (uint64_t)nf * ad_blk_stride(max_out_len) * 4 + 256;   // block start table
 }
 
 extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
@@ -329,10 +330,30 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
                                      uint32_t nf, uint64_t max_in_len, uint64_t max_out_len,
                                      void *ws, hc_stream_t stream)
 {
-    (void)max_in_len; (void)max_out_len; (void)ws;
+    (void)max_in_len;
     if (nf == 0) return 0;
-    HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off,
-              out_cap, out_len, status, nf);
+    if (out && !ws) {
+        // no scratch: one thread per file (slow, kept for callers that cannot provide ws)
+        HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off,
+                  out_cap, out_len, status, nf, (i32)-1);
+        HC_CHECK_LAUNCH();
+        return 0;
+    }
+    const u64 bs = ad_blk_stride(max_out_len);
+    HC_LAUNCH(adapt_index_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out_cap, out != nullptr,
+              (u32 *)ws, bs, out_len, status, nf);
+    HC_CHECK_LAUNCH();
+    if (!out) return 0;
+    u64 chunks = max_out_len / (64 * 1024);
+    if (chunks < 1) chunks = 1;
+    u64 want = (592 * 2 + nf - 1) / nf;
+    if (chunks > want) chunks = want;
+    HC_LAUNCH(adapt_expand_kernel, grid2(chunks, nf), dim3(AD_EXP_TPB), 0, stream, in, in_off, in_len, (const u32 *)ws, bs,
+              out, out_off, (const i32 *)status, nf);
+    HC_CHECK_LAUNCH();
+    // headers with more blocks than the table holds (block size < 8) take the serial decoder
+    HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off, out_cap,
+              out_len, status, nf, (i32)AD_ST_SERIAL);
     HC_CHECK_LAUNCH();
     return 0;
 }
@@ -617,8 +638,9 @@ static int dec_expand(hc_codec *c, uint32_t nf, uint64_t max_sym_len, uint64_t m
     }
     if (kinds & HC_KIND_ADAPT) {
         // non-adaptive files carry length 0 here (status 10 for them is ignored by the merge)
+        if (d_out) HC_TRY(c->ws.ensure((size_t)hc_adapt_decode_ws_bytes(nf, max_out_len)));
         HC_TRY(hc_adapt_decode_batch((const u8 *)c->a.p, t.u64_at(T_OFF_A), t.u64_at(T_LEN_AD), d_out, d_out_off, d_out_cap,
-                                     t.u64_at(T_N_AD), t.i32_at(T_ST2), nf, max_sym_len, max_out_len, nullptr, s));
+                                     t.u64_at(T_N_AD), t.i32_at(T_ST2), nf, max_sym_len, max_out_len, d_out ? c->ws.p : nullptr, s));
         stage_mark(c, d_out ? "adapt_decode" : "adapt_decode_size");
     }
     HC_LAUNCH(decompress_merge_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, (const u8 *)t.u8_at(T_FLAGS),

@@ -113,6 +113,20 @@ HC_DEV u32 vsub4(u32 a, u32 b)
 HC_DEV u32 atomic_add(u32 *p, u32 v) { u32 o = *p; *p = o + v; return o; }
 HC_DEV u64 atomic_add64(u64 *p, u64 v) { u64 o = *p; *p = o + v; return o; }
 HC_DEV void atomic_max_i32(i32 *p, i32 v) { if (v > *p) *p = v; }
+// "shared-space addresses": offsets from an arena base (the kernel's __shared__ object)
+inline unsigned char *g_emu_smem_base = nullptr;
+#define HC_SMEM_ARENA(obj) (hcd::g_emu_smem_base = (unsigned char *)&(obj) - 64)
+HC_DEV u32 smem_addr(const void *p) { return (u32)((const unsigned char *)p - g_emu_smem_base); }
+HC_DEV uint2 lds64(u32 a) { uint2 v; memcpy(&v, g_emu_smem_base + a, 8); return v; }
+HC_DEV u32 lds32(u32 a) { u32 v; memcpy(&v, g_emu_smem_base + a, 4); return v; }
+HC_DEV u32 lds16(u32 a) { u16 v; memcpy(&v, g_emu_smem_base + a, 2); return v; }
+HC_DEV u32 lds8(u32 a) { return g_emu_smem_base[a]; }
+HC_DEV void sts64(u32 a, uint2 v) { memcpy(g_emu_smem_base + a, &v, 8); }
+HC_DEV void sts32(u32 a, u32 v) { memcpy(g_emu_smem_base + a, &v, 4); }
+HC_DEV void sts16(u32 a, u32 v) { u16 t = (u16)v; memcpy(g_emu_smem_base + a, &t, 2); }
+HC_DEV void sts8(u32 a, u32 v) { g_emu_smem_base[a] = (u8)v; }
+HC_DEV u32 funnel_r(u32 lo, u32 hi, u32 sh) { return (u32)((((u64)hi << 32) | lo) >> (sh & 31)); }
+HC_DEV void sts32_if(bool p, u32 a, u32 v) { if (p) sts32(a, v); }
 HC_DEV uint4 ldg16(const void *p) { uint4 v; memcpy(&v, p, 16); return v; }
 HC_DEV uint4 ldg16_rw(const void *p) { uint4 v; memcpy(&v, p, 16); return v; }
 HC_DEV void stg16(void *p, uint4 v) { memcpy(p, &v, 16); }
@@ -151,6 +165,29 @@ HC_DEV u32 vsub4(u32 a, u32 b) { return __vsub4(a, b); }
 HC_DEV u32 atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
 HC_DEV u64 atomic_add64(u64 *p, u64 v) { return atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 HC_DEV void atomic_max_i32(i32 *p, i32 v) { atomicMax(p, v); }
+// shared-space (32-bit) addressing: tree links are stored as shared addresses so that a walk
+// needs no address arithmetic between dependent loads
+#define HC_SMEM_ARENA(obj) ((void)0)
+HC_DEV u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+HC_DEV uint2 lds64(u32 a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+HC_DEV u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+HC_DEV u32 lds16(u32 a) { u32 v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+HC_DEV u32 lds8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+HC_DEV void sts64(u32 a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+HC_DEV void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+HC_DEV void sts16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+HC_DEV void sts8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+HC_DEV u32 funnel_r(u32 lo, u32 hi, u32 sh) { return __funnelshift_r(lo, hi, sh); }
+// predicated store: no branch, no divergence (used for "lane 0 is the only writer")
+HC_DEV void sts32_if(bool p, u32 a, u32 v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u32 [%0], %1; }" :: "r"(a), "r"(v), "r"((u32)p) : "memory");
+}
 // streaming 16-byte load: read-only path, do not allocate in L1 (data is touched once)
 HC_DEV uint4 ldg16(const void *p)
 {

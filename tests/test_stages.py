@@ -210,16 +210,27 @@ def test_adapt_decode(be, oracle):
     for (w, h, im) in imgs[:6]:
         encs.append(oracle.adapt_encode_bs(im, w, h, 8))
         imgs = imgs + [(w, h, im)]
+    # a stream with block size 4 (never produced by the reference encoder, accepted by its decoder)
+    img4 = synth.image("walk", 12, 77, 8).reshape(-1)
+    encs.append(oracle.adapt_encode_bs(img4, 12, 8, 4))
+    imgs = imgs + [(12, 8, img4)]
     src = Batch(be, [e.size for e in encs], encs)
-    dst = Batch(be, [w * h for w, h, _ in imgs], fill=0xEE)
-    st = be.upload(np.zeros(src.nf, np.int32))
-    rc0(be.L.hc_adapt_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
-                                   dst.d_len.ptr, st.ptr, src.nf, src.max_len, 0, None, be.stream))
-    assert not be.download(st, src.nf * 4, np.int32).any()
-    lens = dst.lens()
-    for i, ((w, h, im), g) in enumerate(zip(imgs, dst.files(lens))):
-        assert int(lens[i]) == w * h
-        assert np.array_equal(g, im), (w, h, i)
+    max_out = max(w * h for w, h, _ in imgs)
+    for use_ws in (True, False):      # parallel index+expand kernels / serial fallback without scratch
+        dst = Batch(be, [w * h for w, h, _ in imgs], fill=0xEE)
+        st = be.upload(np.zeros(src.nf, np.int32))
+        ws = be.alloc(be.L.hc_adapt_decode_ws_bytes(src.nf, max_out)) if use_ws else None
+        # size query first (out == NULL)
+        rc0(be.L.hc_adapt_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, None, None, None, dst.d_len.ptr, st.ptr,
+                                       src.nf, src.max_len, max_out, None, be.stream))
+        assert [int(x) for x in dst.lens()] == [w * h for w, h, _ in imgs]
+        rc0(be.L.hc_adapt_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                       dst.d_len.ptr, st.ptr, src.nf, src.max_len, max_out, ws.ptr if ws else None, be.stream))
+        assert not be.download(st, src.nf * 4, np.int32).any()
+        lens = dst.lens()
+        for i, ((w, h, im), g) in enumerate(zip(imgs, dst.files(lens))):
+            assert int(lens[i]) == w * h
+            assert np.array_equal(g, im), (w, h, i, use_ws)
 
 
 def test_adapt_decode_errors(be, oracle):
@@ -239,12 +250,14 @@ def test_adapt_decode_errors(be, oracle):
     for c, e in zip(cases[:5], expect[:5]):
         assert oracle.adapt_decode(c)[0] == e
     src = Batch(be, [c.size for c in cases], cases)
-    dst = Batch(be, [16 * 24] * len(cases))
-    st = be.upload(np.zeros(src.nf, np.int32))
-    rc0(be.L.hc_adapt_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
-                                   dst.d_len.ptr, st.ptr, src.nf, src.max_len, 0, None, be.stream))
-    assert list(be.download(st, src.nf * 4, np.int32)) == expect
-    assert np.array_equal(dst.files(dst.lens())[-1], img)
+    for use_ws in (True, False):
+        dst = Batch(be, [16 * 24] * len(cases))
+        st = be.upload(np.zeros(src.nf, np.int32))
+        ws = be.alloc(be.L.hc_adapt_decode_ws_bytes(src.nf, 16 * 24)) if use_ws else None
+        rc0(be.L.hc_adapt_decode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                       dst.d_len.ptr, st.ptr, src.nf, src.max_len, 16 * 24, ws.ptr if ws else None, be.stream))
+        assert list(be.download(st, src.nf * 4, np.int32)) == expect, use_ws
+        assert np.array_equal(dst.files(dst.lens())[-1], img)
 
 
 def _fgk_inputs(be):
