@@ -194,6 +194,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import hc_b200
+    import shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -232,7 +233,6 @@ def run_ours(args):
     d_dec = torch.empty(nf * FILE_BYTES + 512, dtype=torch.uint8, device=dev)
     d_dec_len = torch.zeros(nf, dtype=i64, device=dev)
     d_st_d = torch.zeros(nf, dtype=torch.int32, device=dev)
-    sizes_all = torch.zeros(world * nf, dtype=i64, device=dev)
     max_sym = m_bound
     kinds = hc_b200.KIND_DIFF | (hc_b200.KIND_ADAPT if use_adapt else hc_b200.KIND_PLAIN)
 
@@ -249,11 +249,8 @@ def run_ours(args):
     def gather_sizes():
         # the path's only collective: per-file output sizes -> global offsets table
         with torch.cuda.stream(stream):
-            if world > 1:
-                dist.all_gather_into_tensor(sizes_all, d_cmp_len)
-            else:
-                sizes_all.copy_(d_cmp_len)
-            return torch.cumsum(sizes_all, 0) - sizes_all
+            sizes = shard.gather_sizes(d_cmp_len, nf * world)
+            return shard.global_offsets(sizes, 16)[0]
 
     def step_dev():
         compress_dev()
@@ -304,8 +301,6 @@ def run_ours(args):
     t1 = time.perf_counter()
     launches = L.hc_launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
-    # split of the last step: events recorded after compress of step k
-    ms_comp_last = (evc[-2].elapsed_time(evc[-1]) if len(evc) > 1 else None)
     tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -438,7 +433,6 @@ def run_ours(args):
                    "files_per_gpu": nf, "bytes_per_gpu": n_in, "l2": "inputs (%.2f GiB per GPU) larger than L2, no flush needed" % (n_in / 2 ** 30),
                    "parallelism": "files sharded over %d GPU(s); NCCL all-gather of per-file sizes" % world},
         "bpc": 8.0 * out_bytes / n_in, "compressed_bytes_rank0": out_bytes, "parity_checked_files": parity_files,
-        "compress_ms_last_step": None if ms_comp_last is None else None,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "fgk": fgk, "cpu_baseline": cpu,
         "stage_ms": {"compress": st_cmp, "decompress": st_dec}, "gen_seconds": t_gen,
     }

@@ -280,6 +280,15 @@ HC_DEV u64 bw_finish(BitWriter &b, u32 lane)
     return total;
 }
 
+// File handled by warp `wid` of CTA `b`.  Warp w of a CTA issues from SM sub-partition w % 4; batches
+// are often periodic in entropy class (bench: class = i mod 4), and with the identity mapping every
+// long (high-entropy) stream would sit on the same scheduler of every SM while the other three idle
+// once the short streams have finished.  Rotating by the CTA index spreads any such period.
+HC_DEV u32 fgk_file_of(u32 b, u32 wid)
+{
+    return b * FGK_WARPS + ((wid + b + (b >> 2) + (b >> 4)) & (FGK_WARPS - 1));
+}
+
 HC_KERNEL HC_LAUNCH_BOUNDS(FGK_WARPS * 32, 1)
 fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, const u64 *HC_RESTRICT sym_len,
                   const u8 *HC_RESTRICT flags, u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off,
@@ -288,7 +297,7 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
     HC_SHARED FgkTree trees[FGK_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 f = blockIdx.x * FGK_WARPS + wid;
+    const u32 f = fgk_file_of(blockIdx.x, wid);
     if (f >= nf) return;
     FgkCtx c;
     fgk_init(c, trees[wid], lane);
@@ -407,7 +416,7 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     HC_SHARED FgkTree trees[FGK_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 f = blockIdx.x * FGK_WARPS + wid;
+    const u32 f = fgk_file_of(blockIdx.x, wid);
     if (f >= nf) return;
     FgkCtx c;
     fgk_init(c, trees[wid], lane);
