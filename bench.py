@@ -47,9 +47,12 @@ METRIC = "compress+decompress throughput, batched 512x512 RAW -m -a"
 UNIT = "GB/s"
 
 
+_CLASSES = tuple(os.environ.get("HC_BENCH_CLASSES", ",".join(synth.CLASSES)).split(","))   # experiments only
+
+
 def _gen_one(args):
     i, seed0 = args
-    return synth.image(synth.CLASSES[i % 4], N_SIDE, seed0 + i).reshape(-1)
+    return synth.image(_CLASSES[i % len(_CLASSES)], N_SIDE, seed0 + i).reshape(-1)
 
 
 def make_batch(count, seed0, procs):

@@ -29,7 +29,10 @@
 
 namespace hcd {
 
-constexpr int FGK_WARPS = 4;             // streams per CTA
+#ifndef HC_FGK_WARPS
+#define HC_FGK_WARPS 4
+#endif
+constexpr int FGK_WARPS = HC_FGK_WARPS;  // streams per CTA (4 = one per SM sub-partition; measured best on B200)
 constexpr u32 FGK_ROOT = 512;
 constexpr u32 FGK_NSLOT = 514;           // slots 0..512 + one sentinel (weight 0xffffffff)
 constexpr u32 FGK_LEAF_NYT = (256u << 1) | 1u;
@@ -280,15 +283,6 @@ HC_DEV u64 bw_finish(BitWriter &b, u32 lane)
     return total;
 }
 
-// File handled by warp `wid` of CTA `b`.  Warp w of a CTA issues from SM sub-partition w % 4; batches
-// are often periodic in entropy class (bench: class = i mod 4), and with the identity mapping every
-// long (high-entropy) stream would sit on the same scheduler of every SM while the other three idle
-// once the short streams have finished.  Rotating by the CTA index spreads any such period.
-HC_DEV u32 fgk_file_of(u32 b, u32 wid)
-{
-    return b * FGK_WARPS + ((wid + b + (b >> 2) + (b >> 4)) & (FGK_WARPS - 1));
-}
-
 HC_KERNEL HC_LAUNCH_BOUNDS(FGK_WARPS * 32, 1)
 fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, const u64 *HC_RESTRICT sym_len,
                   const u8 *HC_RESTRICT flags, u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off,
@@ -297,7 +291,7 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
     HC_SHARED FgkTree trees[FGK_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 f = fgk_file_of(blockIdx.x, wid);
+    const u32 f = blockIdx.x * FGK_WARPS + wid;
     if (f >= nf) return;
     FgkCtx c;
     fgk_init(c, trees[wid], lane);
@@ -416,7 +410,7 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     HC_SHARED FgkTree trees[FGK_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 f = fgk_file_of(blockIdx.x, wid);
+    const u32 f = blockIdx.x * FGK_WARPS + wid;
     if (f >= nf) return;
     FgkCtx c;
     fgk_init(c, trees[wid], lane);

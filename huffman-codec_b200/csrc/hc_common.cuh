@@ -13,6 +13,7 @@
 #define HC_DEV static inline
 #define HC_HD static inline
 #define HC_DEVM inline
+#define HC_DEV_NOINLINE static __attribute__((noinline))
 #define HC_SHARED static
 #define HC_DYN_SMEM(name) unsigned char *name = (unsigned char *)hc_emu::dyn_smem()
 #define HC_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
@@ -29,6 +30,7 @@
 #define HC_DEV __device__ __forceinline__
 #define HC_HD __host__ __device__ __forceinline__
 #define HC_DEVM __device__ __forceinline__
+#define HC_DEV_NOINLINE __device__ __noinline__
 #define HC_SHARED __shared__
 #define HC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define HC_LAUNCH(kern, grid, block, smem, stream, ...)                                   \

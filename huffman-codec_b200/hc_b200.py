@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhc_b200.so")
+LIB_PATH = os.environ.get("HC_B200_LIB", os.path.join(HERE, "libhc_b200.so"))   # override: kernel experiments only
 
 u8p = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)

@@ -158,3 +158,63 @@ def test_cross_decode_with_reference_binary(samples):
                 assert np.array_equal(ref_out, ours[0])
                 back, st = cd.decompress([ref_out])
                 assert st[0] == 0 and np.array_equal(back[0], data)
+
+
+@pytest.mark.gpu
+def test_large_images_4096(oracle):
+    """BASELINE config 4 geometry: 4096x4096, -m -a -w 4096 (block sizes up to 1024), one image per
+    low/medium entropy class plus a 1024x1024 random image; byte identical to the oracle."""
+    cd = hc_b200.Codec(0)
+    files, widths = [], []
+    for i, kind in enumerate(("smooth", "const", "walk")):
+        files.append(synth.image(kind, 4096, 2000 + i).reshape(-1))
+        widths.append(4096)
+    files.append(synth.image("random", 1024, 2003).reshape(-1))
+    widths.append(1024)
+    outs, st = cd.compress(files, diff=True, adapt=True, width=widths)
+    assert not st.any()
+    for f, w, o in zip(files, widths, outs):
+        rc, exp = oracle.compress(f, diff=True, adapt=True, width=w, mode=1)
+        assert rc == 0 and o.size == exp.size and np.array_equal(o, exp), w
+    back, st = cd.decompress(outs)
+    assert not st.any()
+    for f, b in zip(files, back):
+        assert np.array_equal(f, b)
+    # plain RLE path on a 16 MiB file (segmented diff kernels, long CTA streams)
+    outs, st = cd.compress(files[:1], diff=True, adapt=False)
+    rc, exp = oracle.compress(files[0], diff=True, adapt=False, mode=1)
+    assert st[0] == 0 and np.array_equal(outs[0], exp)
+    back, st = cd.decompress(outs)
+    assert st[0] == 0 and np.array_equal(back[0], files[0])
+
+
+@pytest.mark.gpu
+def test_cli_matches_reference_cli(samples, golden):
+    """The huffman-codec binary of this repo against the reference CLI contract."""
+    cli = os.path.join(os.path.dirname(hc_b200.HERE), "huffman-codec_b200", "huffman-codec")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        p_in, p_out, p_dec = (os.path.join(tmp, x) for x in ("hd01.raw", "hd01.out", "hd01.dec"))
+        open(p_in, "wb").write(bytes(samples["hd01"]))
+        for mode, flags in (("plain", []), ("ma", ["-m", "-a", "-w", "512"])):
+            r = subprocess.run([cli, "-c"] + flags + ["-i", p_in, "-o", p_out], capture_output=True)
+            out = open(p_out, "rb").read()
+            g = golden["samples"]["hd01"][mode]
+            assert r.returncode == 0 and (len(out), _sha(out)) == (g["size"], g["sha256"])
+            assert r.stderr.decode() == "writing %d bytes to %s\n" % (len(out), p_out)
+            r = subprocess.run([cli, "-d", "-i", p_out, "-o", p_dec], capture_output=True)
+            assert r.returncode == 0 and open(p_dec, "rb").read() == bytes(samples["hd01"])
+        # error behaviour: same exit codes and stderr text as the reference binary
+        for c in golden["cli"]:
+            if "malformed" in c:
+                bad = os.path.join(tmp, "bad.out")
+                open(bad, "wb").write(bytes.fromhex(c["blob"]))
+                r = subprocess.run([cli, "-d", "-i", bad, "-o", os.path.join(tmp, "o")], capture_output=True)
+            else:
+                small = os.path.join(tmp, "small.raw")
+                open(small, "wb").write(bytes(range(30)))
+                r = subprocess.run([cli] + [a.replace("$TMP", tmp) for a in c["args"]], capture_output=True, cwd=tmp)
+                assert r.stdout.decode() == c["stdout"]
+            assert r.returncode == c["rc"], c
+            assert r.stderr.decode() == c["stderr"].replace("$TMP", tmp), c
