@@ -386,11 +386,17 @@ def run_ours(args):
         if name in alg and ms > 0:
             a = alg[name] / (ms * 1e-3) / 1e9
             stages.append({"kernel": name, "ms": ms, "algorithmic_bytes": alg[name], "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak})
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and nf == 4096 and use_adapt:       # per-launch DRAM bytes from the committed ncu capture
+        traffic = json.load(open(tpath))
+    for st in stages:
+        st["traffic"] = traffic.get(st["kernel"])
     dom = max(stages, key=lambda s: s["ms"]) if stages else None
     roofline = None
     if dom:
         roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": dom.get("traffic"), "peak_source": peak_src,
                     "note": "the dominant kernel is FGK: serial per stream, latency/issue bound (one warp per file), so its HBM fraction is "
                             "structurally tiny; the HBM-bound transform kernels are listed in `stages`",
                     "stages": stages}
