@@ -384,12 +384,24 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
             u64 produced = 0;
             u32 state = 0, prev_last = 0;
             while (produced < req) {
-                const u64 idx = pos + lane;
-                const bool valid = idx < m;
-                const u32 b = valid ? src[idx] : 0u;
-                u32 pb = shfl_up(b, 1);
+                // 128 tokens per step: 4 consecutive bytes per lane
+                const u64 idx = pos + 4u * lane;
+                u32 b[4], nv = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const bool v = idx + k < m;
+                    b[k] = v ? src[idx + k] : 0u;
+                    nv += v ? 1u : 0u;
+                }
+                u32 pb = shfl_up(b[3], 1);
                 if (lane == 0) pb = prev_last;
-                u32 map = !valid ? MAP_ID : (b == pb ? MAP_EQ : MAP_NE);
+                // decoder state map of the lane's (valid) bytes
+                u32 map = MAP_ID, pr = pb;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if ((u32)k < nv) map = map_compose(map, b[k] == pr ? MAP_EQ : MAP_NE);
+                    pr = b[k];
+                }
                 u32 inc = map;
                 for (int d = 1; d < 32; d <<= 1) {
                     u32 t = shfl_up(inc, d);
@@ -397,28 +409,55 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
                 }
                 u32 exm = shfl_up(inc, 1);
                 if (lane == 0) exm = MAP_ID;
-                const u32 st_before = map_apply(exm, state);
-                u32 len = !valid ? 0u : (st_before == 3u ? b : 1u);
-                u32 cum = len;
+                // output length of each of the lane's tokens
+                u32 s = map_apply(exm, state), len[4], sum = 0;
+                pr = pb;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    len[k] = 0;
+                    if ((u32)k < nv) {
+                        if (s == 3u) { len[k] = b[k]; s = 0; }
+                        else { len[k] = 1; s = (s == 0u) ? 1u : (b[k] == pr ? s + 1u : 1u); }
+                    }
+                    pr = b[k];
+                    sum += len[k];
+                }
+                u32 cum = sum;
                 for (int d = 1; d < 32; d <<= 1) {
                     u32 t = shfl_up(cum, d);
                     if (lane >= (u32)d) cum += t;
                 }
                 const u64 rem = req - produced;
-                const u32 vmask = ballot(valid);
-                const u32 hit = ballot(valid && (u64)cum >= rem);
+                const u32 hit = ballot(nv != 0u && (u64)cum >= rem);
                 if (hit == 0u) {
-                    const u32 nvalid = (u32)popc(vmask);
-                    if (nvalid == 0u) { err = 14; break; }              // src/transform.cpp:170-174
-                    produced += shfl(cum, (int)nvalid - 1);
-                    state = map_apply(shfl(inc, (int)nvalid - 1), state);
-                    prev_last = shfl(b, (int)nvalid - 1);
-                    pos += nvalid;
-                    if (nvalid < 32u && produced < req) { err = 14; break; }
+                    // the step did not complete the block: consume every valid token
+                    u32 tv = nv;
+                    for (int d = 16; d > 0; d >>= 1) tv += shfl_xor(tv, d);
+                    if (tv == 0u) { err = 14; break; }                  // src/transform.cpp:170-174
+                    produced += shfl(cum, 31);
+                    state = map_apply(shfl(inc, 31), state);
+                    const u32 last_lane = (tv - 1u) >> 2;
+                    {
+                        // byte value of the last consumed token (lane last_lane, slot (tv-1)&3)
+                        const u32 slot = (tv - 1u) & 3u;
+                        const u32 mine = slot == 0 ? b[0] : slot == 1 ? b[1] : slot == 2 ? b[2] : b[3];
+                        prev_last = shfl(mine, (int)last_lane);
+                    }
+                    pos += tv;
+                    if (tv < 128u && produced < req) { err = 14; break; }
                 } else {
-                    const int e = ffs(hit) - 1;
-                    if ((u64)shfl(cum, e) > rem) { err = 13; break; }   // src/transform.cpp:180-184
-                    pos += (u32)e + 1u;
+                    // the block ends inside lane `hl`: find the token
+                    const int hl = ffs(hit) - 1;
+                    const u32 before = shfl(cum - sum, hl);               // produced by the lanes before hl
+                    const u32 l0 = shfl(len[0], hl), l1 = shfl(len[1], hl), l2 = shfl(len[2], hl), l3 = shfl(len[3], hl);
+                    const u64 need = rem - before;                        // still missing when lane hl starts (>= 1)
+                    u32 tok, got;
+                    if ((u64)l0 >= need) { tok = 0; got = l0; }
+                    else if ((u64)l0 + l1 >= need) { tok = 1; got = l0 + l1; }
+                    else if ((u64)l0 + l1 + l2 >= need) { tok = 2; got = l0 + l1 + l2; }
+                    else { tok = 3; got = l0 + l1 + l2 + l3; }
+                    if ((u64)got > need) { err = 13; break; }            // src/transform.cpp:180-184
+                    pos += 4u * (u32)hl + tok + 1u;
                     produced = req;
                 }
             }

@@ -439,8 +439,10 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     i32 err = 0;
     u32 count = 0;
     for (u64 i = 0; i < m; i++) {
-        // walk down on a private copy of the window's top 32 bits, consume them afterwards
-        u32 d = root_down, k = lds32(d), t = (u32)(br.win >> 32), len = 0;
+        // walk down on a private copy of the window's top 32 bits, consume them afterwards.  Lane j
+        // remembers the node reached after j+1 steps: the walk visits exactly the nodes the update
+        // will increment, so the update needs no second (leaf->root) chase.
+        u32 d = root_down, k = lds32(d), t = (u32)(br.win >> 32), len = 0, depth = 0, dk = 0;
         while (!(k & 1u)) {
             if (len == 32u) {                            // code longer than 32 bits (very deep tree)
                 if (br.avail < 32u) { err = 9; break; }
@@ -449,8 +451,10 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                 len = 0;
             }
             d = k + ((t >> 31) << 2);
+            if (lane == depth) dk = d;
             t <<= 1;
             len++;
+            depth++;
             k = lds32(d);
         }
         if (err) break;
@@ -458,22 +462,43 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             if (br.avail < len) { err = 9; break; }      // ran out of bits inside a code
             br_skip(br, len, lane);
         }
-        u32 y, a;
+        count++;
+        u32 y;
+        bool moved = false;
         if (k == FGK_LEAF_NYT) {
             if (br.avail < 8u) { err = 9; break; }
             y = br_get(br, 8, lane);
             // a raw symbol that is already in the tree is still decoded as that symbol
             // (src/huffman.cpp:74-86); the update then starts from its existing leaf
             const u32 ex = lds16(c.slot_of + 2u * y);
-            a = ex == 0xffffu ? fgk_split(c, y, lane) : c.up + 8u * ex;
+            const u32 a = ex == 0xffffu ? fgk_split(c, y, lane) : c.up + 8u * ex;
+            if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
+            fgk_update_plain(c, a, lane, count, 0x1ffu, moved);          // ends with a warp barrier
         } else {
             y = k >> 1;
-            a = fgk_up_of(c, d);
+            if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
+            if (depth <= 32u) {
+                // all levels at once, one lane per level (lane depth-1 = the leaf): a level whose next
+                // slot carries the same weight needs leader search / swap and everything above it may
+                // move, so the sequential walk takes over from the deepest such level.
+                const bool valid = lane < depth;
+                const u32 A = valid ? fgk_up_of(c, dk) : c.sentinel - 8u;
+                const u32 W = lds32(A), w1 = lds32(A + 8u);
+                const u32 tm = ballot(valid && w1 == W);
+                FGK_LEVEL_SYNC();
+                if (tm == 0u) {
+                    sts32_if(valid, A, W + 1u);
+                    sts32_if(lane == 0, c.root, count);
+                    syncwarp();
+                } else {
+                    const u32 k0 = 31u - (u32)clz(tm);                   // deepest level with a tie
+                    sts32_if(valid && lane > k0, A, W + 1u);             // plain levels below it
+                    fgk_update_plain(c, shfl(A, (int)k0), lane, count, 0x1ffu, moved);
+                }
+            } else {
+                fgk_update_plain(c, fgk_up_of(c, d), lane, count, 0x1ffu, moved);
+            }
         }
-        count++;
-        if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
-        bool moved = false;
-        fgk_update_plain(c, a, lane, count, 0x1ffu, moved);   // ends with a warp barrier
         if ((i & 127u) == 127u) {
             stg32_stream(dst + (i >> 7) * 32u + lane, lds32(c.buf + 4u * lane));
             syncwarp();

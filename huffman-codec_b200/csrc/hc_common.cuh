@@ -112,12 +112,21 @@ HC_DEV u32 vsub4(u32 a, u32 b)
     for (int i = 0; i < 4; i++) r |= (u32)(u8)((a >> (8 * i)) - (b >> (8 * i))) << (8 * i);
     return r;
 }
+HC_DEV u32 vcmpeq4(u32 a, u32 b)
+{
+    u32 r = 0;
+    for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xffu) == ((b >> (8 * i)) & 0xffu)) r |= 0xffu << (8 * i);
+    return r;
+}
+HC_DEV u32 funnel_l(u32 lo, u32 hi, u32 sh) { return sh & 31 ? (hi << (sh & 31)) | (lo >> (32 - (sh & 31))) : hi; }
 HC_DEV u32 atomic_add(u32 *p, u32 v) { u32 o = *p; *p = o + v; return o; }
 HC_DEV u64 atomic_add64(u64 *p, u64 v) { u64 o = *p; *p = o + v; return o; }
 HC_DEV void atomic_max_i32(i32 *p, i32 v) { if (v > *p) *p = v; }
 // "shared-space addresses": offsets from an arena base (the kernel's __shared__ object)
 inline unsigned char *g_emu_smem_base = nullptr;
-#define HC_SMEM_ARENA(obj) (hcd::g_emu_smem_base = (unsigned char *)&(obj) - 64)
+// base = start of the 4 GiB window that holds the kernel's static "shared" objects, so that every
+// one of them has a positive 32-bit offset
+#define HC_SMEM_ARENA(obj) (hcd::g_emu_smem_base = (unsigned char *)((uintptr_t)&(obj) & ~(uintptr_t)0xffffffffull))
 HC_DEV u32 smem_addr(const void *p) { return (u32)((const unsigned char *)p - g_emu_smem_base); }
 HC_DEV uint2 lds64(u32 a) { uint2 v; memcpy(&v, g_emu_smem_base + a, 8); return v; }
 HC_DEV u32 lds32(u32 a) { u32 v; memcpy(&v, g_emu_smem_base + a, 4); return v; }
@@ -164,6 +173,8 @@ HC_DEV u64 bswap64(u64 v)
 }
 HC_DEV u32 vadd4(u32 a, u32 b) { return __vadd4(a, b); }
 HC_DEV u32 vsub4(u32 a, u32 b) { return __vsub4(a, b); }
+HC_DEV u32 vcmpeq4(u32 a, u32 b) { return __vcmpeq4(a, b); }
+HC_DEV u32 funnel_l(u32 lo, u32 hi, u32 sh) { return __funnelshift_l(lo, hi, sh); }
 HC_DEV u32 atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
 HC_DEV u64 atomic_add64(u64 *p, u64 v) { return atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 HC_DEV void atomic_max_i32(i32 *p, i32 v) { atomicMax(p, v); }

@@ -27,6 +27,107 @@ namespace hcd {
 
 constexpr u32 ENC_STAGE_BYTES = TILE_BYTES + TILE_BYTES / 3 + 64;   // worst case 4/3 + phase
 
+// bit k = (byte k of v == byte k-1), byte -1 = prev (0x100 = none).  Byte-SIMD: one __vcmpeq4 per
+// word against the stream shifted by one byte, then a multiply gathers the 0xFF bytes into bits.
+HC_DEV u32 rle_eq_mask16(const uint4 &v, u32 prev)
+{
+    const u32 K = 0x08040201u;
+    const u32 m0 = vcmpeq4(v.x, (v.x << 8) | (prev & 0xffu));
+    const u32 m1 = vcmpeq4(v.y, funnel_l(v.x, v.y, 8));
+    const u32 m2 = vcmpeq4(v.z, funnel_l(v.y, v.z, 8));
+    const u32 m3 = vcmpeq4(v.w, funnel_l(v.z, v.w, 8));
+    const u32 lo8 = (((m0 & K) | ((m1 & K) << 4)) * 0x01010101u) >> 24;
+    const u32 hi8 = (((m2 & K) | ((m3 & K) << 4)) * 0x01010101u) >> 24;
+    u32 e = lo8 | (hi8 << 8);
+    if (prev > 0xffu) e &= ~1u;
+    return e;
+}
+
+// Output of one 16-element vector.  e: equality bits 0..16 (bit 16 = the element after the vector),
+// valid: bits of existing elements, k0: run index of element 0 if it continues a run (else unused).
+//   lit bit k  : element k emits its byte          (run index q < 3)
+//   cnt bit k  : element k emits a count byte      (last of its run, 2 <= q < 257)
+// Fast path (no element can reach run index 257): pure bit logic, see SURVEY.md A.3.
+// Returns false if the vector needs the scalar path (a run of >= 257 elements passes through it).
+HC_DEV bool rle_vec_masks(u32 e, u32 valid, u32 &k0, u32 &lit, u32 &cnt)
+{
+    const bool cont = e & 1u;
+    if (cont && k0 + 16u >= 257u) {
+        // inside a long run: the index wraps at 258 (src/transform.cpp:259-263).  Reduce it; the bit
+        // logic below stays exact as long as the leading segment of this vector neither restarts
+        // (q < 3 again) nor reaches q == 257.
+        const u32 r0 = k0 % 258u;
+        const u32 p = (u32)ffs((~e & 0xffffu) | 0x10000u) - 1u;   // elements (0..16) that continue the incoming run
+        if (r0 < 3u || r0 + p > 257u) return false;
+        k0 = r0;
+    }
+    const u32 b1 = (cont && k0 >= 2u) ? 2u : 0u, b2 = (cont && k0 >= 3u) ? 1u : 0u;
+    const u32 x = ((e & 0xffffu) << 2) | b1 | b2;     // bit k+2 = e_k, bits 1,0 = e_-1, e_-2
+    const u32 q2 = (x >> 2) & (x >> 1);               // e_k & e_k-1           (q >= 2)
+    const u32 q3 = q2 & x;                            // ... & e_k-2           (q >= 3)
+    lit = valid & ~q3;
+    cnt = valid & q2 & ~(e >> 1);                     // run ends here (next element does not continue)
+    return true;
+}
+
+// run index of element k inside a vector (fast path only: no wrap inside the vector)
+HC_DEV u32 rle_run_index(u32 e, u32 k0, u32 k)
+{
+    const u32 zeros = ~e & ((2u << k) - 1u);          // run starts at or below k
+    return zeros ? k - (31u - (u32)clz(zeros)) : k0 + k;
+}
+
+// byte-granular writer into the shared staging buffer: words are assembled in a 64-bit register,
+// full words go out as STS.32, the ragged first/last bytes as STS.U8 (neighbouring threads own the
+// other bytes of those words)
+struct StageWriter {
+    u64 buf;
+    u32 fill;      // bytes in buf (including the leading filler of the first word)
+    u32 waddr;     // shared address of the word being assembled
+    u32 skip;      // filler bytes of the first word still to be skipped (0 after the first flush)
+};
+
+HC_DEV void sw_init(StageWriter &w, u32 stage_addr, u32 o)
+{
+    w.buf = 0;
+    w.fill = o & 3u;
+    w.skip = o & 3u;
+    w.waddr = stage_addr + (o & ~3u);
+}
+
+HC_DEV void sw_flush_word(StageWriter &w)
+{
+    const u32 word = (u32)w.buf;
+    if (w.skip) {
+        for (u32 i = w.skip; i < 4u; i++) sts8(w.waddr + i, word >> (8u * i));
+        w.skip = 0;
+    } else {
+        sts32(w.waddr, word);
+    }
+    w.waddr += 4u;
+    w.buf >>= 32;
+    w.fill -= 4u;
+}
+
+HC_DEV void sw_put_byte(StageWriter &w, u32 b)
+{
+    w.buf |= (u64)(b & 0xffu) << (8u * w.fill);
+    if (++w.fill >= 4u) sw_flush_word(w);
+}
+
+HC_DEV void sw_put_word(StageWriter &w, u32 x)     // 4 bytes at once
+{
+    w.buf |= (u64)x << (8u * w.fill);
+    w.fill += 4u;
+    sw_flush_word(w);
+}
+
+HC_DEV void sw_finish(StageWriter &w)
+{
+    const u32 word = (u32)w.buf;
+    for (u32 i = w.skip; i < w.fill; i++) sts8(w.waddr + i, word >> (8u * i));
+}
+
 HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
 rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u64 *HC_RESTRICT out_len, u32 nf)
@@ -34,7 +135,9 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     HC_SHARED u32 wtot[2][32];
     HC_SHARED u32 s_carry_run;
     HC_SHARED HC_ALIGNED16 u8 sout[ENC_STAGE_BYTES];
+    HC_SMEM_ARENA(wtot);
     const u32 tid = threadIdx.x, lane = tid & 31;
+    const u32 stage = smem_addr(sout);
 
     for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
         const u64 n = in_len[f];
@@ -62,58 +165,53 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
 #pragma unroll
             for (int j = 0; j < UN; j++) {
                 const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
-                u32 first = cur[j].x & 0xffu, last = cur[j].w >> 24;
+                const u32 first = cur[j].x & 0xffu, last = cur[j].w >> 24;
                 u32 pb = shfl_up(last, 1), nb = shfl_down(first, 1);
                 if (lane == 0) pb = (p > 0 && p < n) ? ldg8(src + p - 1) : 0x100u;
                 if (lane == 31) nb = (p + 16 < n) ? ldg8(src + p + 16) : 0x100u;
-                u32 e = 0, prev = pb;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    u32 b = vec_byte(cur[j], k);
-                    if (b == prev) e |= 1u << k;
-                    prev = b;
-                }
-                if (nb == prev) e |= 1u << 16;
-                u32 vm = p >= n ? 0u : (n - p >= 17 ? 0x1ffffu : ((1u << (u32)(n - p)) - 1u));
-                if (p == 0) e &= ~1u;
+                u32 e = rle_eq_mask16(cur[j], pb);
+                if (nb == last) e |= 1u << 16;
+                const u32 vm = p >= n ? 0u : (n - p >= 17 ? 0x1ffffu : ((1u << (u32)(n - p)) - 1u));
                 // the last element of the file never continues a run (forced literal)
                 if (n - 1 >= p && n - 1 - p <= 16) e &= ~(1u << (u32)(n - 1 - p));
                 e &= vm;
                 eq[j] = e;
                 valid[j] = vm & 0xffffu;
-                u32 starts = valid[j] & ~e;
+                const u32 starts = valid[j] & ~e;
                 // tile-relative position + 1 of the last run start owned by this thread
                 smax[j] = starts ? (u32)j * SUB_BYTES + tid * 16 + (31u - (u32)clz(starts)) + 1u : 0u;
             }
             block_scan_striped(smax, sexcl, 0u, OpMax(), wtot[0]);
 
-            // ---- per-element output counts --------------------------------------------
-            u32 cnt[UN], oexcl[UN];
-            u32 qfirst[UN];   // q of element 0 of the thread's vector
+            // ---- per-vector output masks and counts ----------------------------------------
+            u32 cnt[UN], oexcl[UN], k0v[UN], lit[UN], cbm[UN];
+            u32 slowm = 0;   // bit j: vector j takes the scalar path (a run >= 257 passes through it)
 #pragma unroll
             for (int j = 0; j < UN; j++) {
                 const u32 tp = (u32)j * SUB_BYTES + tid * 16;   // tile-relative position
-                u32 kidx = sexcl[j] ? tp - (sexcl[j] - 1u) : carry_run + tp;
-                if (!(eq[j] & 1u)) kidx = 0;
-                u32 q = kidx % 258u;
-                qfirst[j] = q;
-                u32 c = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    if (k > 0) q = ((eq[j] >> k) & 1u) ? (q == 257u ? 0u : q + 1u) : 0u;
-                    bool v = (valid[j] >> k) & 1u;
-                    bool is_end = !((eq[j] >> (k + 1)) & 1u);   // next element starts a run / is final / absent
-                    u32 ck = (q < 3u ? 1u : 0u) + (q == 257u ? 1u : 0u) + ((is_end && q >= 2u && q != 257u) ? 1u : 0u);
-                    // the final element of the file: exactly one literal (q == 0 there, is_end adds nothing)
-                    c += v ? ck : 0u;
+                const u32 k0 = sexcl[j] ? tp - (sexcl[j] - 1u) : carry_run + tp;   // true run index of element 0
+                u32 kr = k0;                                                      // reduced mod 258 if needed
+                u32 c;
+                if (rle_vec_masks(eq[j], valid[j], kr, lit[j], cbm[j])) {
+                    k0v[j] = kr;
+                    c = (u32)popc(lit[j]) + (u32)popc(cbm[j]);
+                } else {
+                    k0v[j] = k0;
+                    slowm |= 1u << j;
+                    u32 q = k0 % 258u;
+                    c = 0;
+                    for (int k = 0; k < 16; k++) {
+                        if (k > 0) q = ((eq[j] >> k) & 1u) ? (q == 257u ? 0u : q + 1u) : 0u;
+                        const bool is_end = !((eq[j] >> (k + 1)) & 1u);
+                        const u32 ck = (q < 3u ? 1u : 0u) + (q == 257u ? 1u : 0u) + ((is_end && q >= 2u && q != 257u) ? 1u : 0u);
+                        c += ((valid[j] >> k) & 1u) ? ck : 0u;
+                    }
                 }
                 cnt[j] = c;
                 if (j == UN - 1 && tid == TPB - 1) {
-                    // run length at the end of a full tile: q-chain above ended with element 15
-                    // recompute the true (non-modular) length for the carry
-                    u32 kk = kidx;
-                    for (int k = 1; k < 16; k++) kk = ((eq[j] >> k) & 1u) ? kk + 1u : 0u;
-                    s_carry_run = kk + 1u;
+                    // length of the run that ends at the last element of a full tile
+                    const u32 st = valid[j] & ~eq[j];
+                    s_carry_run = st ? 16u - (31u - (u32)clz(st)) : ((eq[j] & 1u) ? k0 + 16u : 16u);
                 }
             }
             u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
@@ -122,19 +220,35 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             const u32 shift = (u32)(out_pos & 15u);
 #pragma unroll
             for (int j = 0; j < UN; j++) {
-                u32 o = shift + oexcl[j];
-                u32 q = qfirst[j];
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    if (k > 0) q = ((eq[j] >> k) & 1u) ? (q == 257u ? 0u : q + 1u) : 0u;
-                    if ((valid[j] >> k) & 1u) {
-                        u32 b = vec_byte(cur[j], k);
-                        bool is_end = !((eq[j] >> (k + 1)) & 1u);
-                        if (q < 3u) sout[o++] = (u8)b;
-                        if (q == 257u) sout[o++] = 255;
-                        else if (is_end && q >= 2u) sout[o++] = (u8)(q - 2u);
+                if (cnt[j] == 0) continue;
+                StageWriter w;
+                sw_init(w, stage, shift + oexcl[j]);
+                if (!((slowm >> j) & 1u)) {
+                    if (lit[j] == 0xffffu && cbm[j] == 0u) {          // all literals: the vector goes out verbatim
+                        sw_put_word(w, cur[j].x); sw_put_word(w, cur[j].y);
+                        sw_put_word(w, cur[j].z); sw_put_word(w, cur[j].w);
+                    } else {
+                        u32 m = lit[j] | cbm[j];
+                        while (m) {
+                            const u32 k = (u32)ffs(m) - 1u;
+                            m &= m - 1u;
+                            if ((lit[j] >> k) & 1u) sw_put_byte(w, vec_byte(cur[j], (int)k));
+                            if ((cbm[j] >> k) & 1u) sw_put_byte(w, rle_run_index(eq[j], k0v[j], k) - 2u);
+                        }
+                    }
+                } else {
+                    u32 q = k0v[j] % 258u;
+                    for (int k = 0; k < 16; k++) {
+                        if (k > 0) q = ((eq[j] >> k) & 1u) ? (q == 257u ? 0u : q + 1u) : 0u;
+                        if ((valid[j] >> k) & 1u) {
+                            const bool is_end = !((eq[j] >> (k + 1)) & 1u);
+                            if (q < 3u) sw_put_byte(w, vec_byte(cur[j], k));
+                            if (q == 257u) sw_put_byte(w, 255u);
+                            else if (is_end && q >= 2u) sw_put_byte(w, q - 2u);
+                        }
                     }
                 }
+                sw_finish(w);
             }
             syncthreads();
             carry_run = s_carry_run;

@@ -337,3 +337,26 @@ def test_offsets_and_gather(be):
     host = be.download(out, int(al.sum()))
     for f, o in zip(files, off):
         assert np.array_equal(host[int(o):int(o) + f.size], f)
+
+
+def test_rle_encode_long_runs(be, oracle):
+    """Runs around the 258 wrap at every phase relative to the 16-byte vectors and 16 KiB tiles."""
+    rng = np.random.default_rng(77)
+    files = []
+    for lead in list(range(0, 20)) + [4090, 16370, 16383]:
+        parts = [rng.integers(0, 256, lead)]
+        for L in (257, 258, 259, 260, 261, 515, 516, 517, 518, 519, 774, 775, 1032, 1033, 3, 2, 4):
+            v = int(rng.integers(0, 256))
+            parts.append(np.full(L + int(rng.integers(0, 3)), v))
+            parts.append(np.array([(v + 1) & 255] * int(rng.integers(1, 4))))
+        files.append(np.concatenate(parts).astype(np.uint8))
+    files.append(np.full(40000, 5, np.uint8))
+    files.append(np.concatenate([np.full(16384 * 2 - 1, 9), np.full(300, 9), np.full(2, 1)]).astype(np.uint8))
+    src = Batch(be, [f.size for f in files], files)
+    dst = Batch(be, [be.L.hc_rle_bound(f.size) for f in files], fill=0xEE)
+    rc0(be.L.hc_rle_encode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_len.ptr,
+                                 src.nf, src.max_len, be.stream))
+    lens = dst.lens()
+    for i, (f, g) in enumerate(zip(files, dst.files(lens))):
+        exp = oracle.rle_encode(f)
+        assert int(lens[i]) == exp.size and np.array_equal(g, exp), (i, f.size)
