@@ -451,6 +451,7 @@ struct hc_codec {
     const char *stage_names[HC_MAX_STAGES];
     int nstages = 0;
     bool ev_ready = false;
+    std::vector<hc_codec *> kids;       // group pipelines of the host-level batch calls (own stream + buffers)
 };
 
 #define HC_TRY(x)                  \
@@ -491,6 +492,8 @@ extern "C" int hc_codec_create(hc_codec **out, int device)
 extern "C" void hc_codec_destroy(hc_codec *c)
 {
     if (!c) return;
+    for (hc_codec *k : c->kids) hc_codec_destroy(k);
+    c->kids.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release();
@@ -708,6 +711,45 @@ struct AsyncFree {   // stream-ordered scratch released on every exit path
     ~AsyncFree() { if (p) cudaFreeAsync(p, s); }
 };
 
+// ---- group pipelines -----------------------------------------------------------------------------
+// The host-level calls split the batch into up to HC_MAX_GROUPS contiguous groups of files, each with
+// its own stream and buffers (a child codec).  Host<->device copies of one group overlap the kernels
+// of the others, and the FGK kernels of all groups are resident together -- that stage is bound by the
+// latency of its longest stream, so running the groups one after another would multiply its time.
+#define HC_MAX_GROUPS 8
+
+static int ensure_kids(hc_codec *c, u32 g)
+{
+    while (c->kids.size() < g) {
+        hc_codec *k = nullptr;
+        int rc = hc_codec_create(&k, c->device);
+        if (rc) return rc;
+        c->kids.push_back(k);
+    }
+    return 0;
+}
+
+static u32 group_count(u32 nf)
+{
+    u32 g = nf / 64;
+    return g < 1 ? 1 : (g > HC_MAX_GROUPS ? HC_MAX_GROUPS : g);
+}
+
+static void group_range(u32 nf, u32 g, u32 ng, u32 *lo, u32 *hi)
+{
+    u32 base = nf / ng, extra = nf % ng;
+    *lo = g * base + (g < extra ? g : extra);
+    *hi = *lo + base + (g < extra ? 1 : 0);
+}
+
+struct GroupJob {
+    u32 lo = 0, hi = 0;
+    AsyncFree dev;
+    u64 *d = nullptr;           // device tables
+    u64 max_a = 0, max_b = 0;   // per-call maxima (meaning depends on the direction)
+    int kinds = 0;
+};
+
 extern "C" int hc_compress_batch(hc_codec *c,
                                  const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
                                  uint32_t nf, int use_diff, int use_adapt, const uint64_t *width_host,
@@ -716,58 +758,86 @@ extern "C" int hc_compress_batch(hc_codec *c,
 {
     if (nf == 0) return 0;
     HC_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    std::vector<u64> d_off;
-    HC_TRY(upload_files(c, c->in, in_base, in_off, in_len, nf, d_off));
-
-    // pinned host tables, 7 x nf: in_off | in_len | width | out_off (strided) | out_cap | compact off | compact len
-    HC_TRY(c->htab.ensure((size_t)nf * 8 * 7));
-    u64 *h = (u64 *)c->htab.p;
-    const size_t N = nf;
-    u64 max_len = 0, pos = 0;
-    for (u32 i = 0; i < nf; i++) {
-        h[i] = d_off[i];
-        h[N + i] = in_len[i];
-        if (in_len[i] > max_len) max_len = in_len[i];
-        u64 w = width_host ? width_host[i] : 512;
-        h[2 * N + i] = w;
-        u64 m_bound = use_adapt ? adapt_bound_from_len(in_len[i]) : hc_rle_bound(in_len[i]);
-        u64 cap = align_up(hc_fgk_bound(m_bound) + 16, HC_ALIGN);
-        h[3 * N + i] = pos;
-        h[4 * N + i] = cap;
-        pos += cap;
+    const u32 ng = group_count(nf);
+    HC_TRY(ensure_kids(c, ng));
+    std::vector<GroupJob> jobs(ng);
+    // phase 1: enqueue upload + the whole compression pipeline of every group
+    for (u32 g = 0; g < ng; g++) {
+        hc_codec *k = c->kids[g];
+        GroupJob &j = jobs[g];
+        group_range(nf, g, ng, &j.lo, &j.hi);
+        const u32 n = j.hi - j.lo;
+        const size_t N = n;
+        cudaStream_t s = k->stream;
+        std::vector<u64> d_off;
+        HC_TRY(upload_files(k, k->in, in_base, in_off + j.lo, in_len + j.lo, n, d_off));
+        // pinned host tables, 9 x n: in_off | in_len | width | out_off (strided) | out_cap | compact off | compact len
+        //                              | out_len (result) | status (result)
+        HC_TRY(k->htab.ensure(N * 8 * 9));
+        u64 *h = (u64 *)k->htab.p;
+        u64 max_len = 0, pos = 0;
+        for (u32 i = 0; i < n; i++) {
+            const u64 len = in_len[j.lo + i];
+            h[i] = d_off[i];
+            h[N + i] = len;
+            if (len > max_len) max_len = len;
+            h[2 * N + i] = width_host ? width_host[j.lo + i] : 512;
+            const u64 m_bound = use_adapt ? adapt_bound_from_len(len) : hc_rle_bound(len);
+            const u64 cap = align_up(hc_fgk_bound(m_bound) + 16, HC_ALIGN);
+            h[3 * N + i] = pos;
+            h[4 * N + i] = cap;
+            pos += cap;
+        }
+        j.max_a = max_len;
+        HC_TRY(k->out.ensure((size_t)pos + 512));
+        j.dev.s = s;
+        HC_CUDA(cudaMallocAsync(&j.dev.p, N * 8 * 9, s));       // 7 tables + out_len + status
+        j.d = (u64 *)j.dev.p;
+        u64 *d = j.d;
+        HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 5, cudaMemcpyHostToDevice, s));
+        HC_TRY(hc_compress_device(k, (const u8 *)k->in.p, d, d + N, d + 2 * N, n, max_len, use_diff, use_adapt,
+                                  (u8 *)k->out.p, d + 3 * N, d + 4 * N, d + 7 * N, (i32 *)(d + 8 * N)));
+        // results come back through PINNED memory: a copy into the caller's (possibly pageable) arrays
+        // would block this loop until the group has finished and serialise the groups
+        HC_CUDA(cudaMemcpyAsync(h + 7 * N, d + 7 * N, N * 8 * 2, cudaMemcpyDeviceToHost, s));
     }
-    HC_TRY(c->out.ensure((size_t)pos + 512));
-    AsyncFree dev;
-    dev.s = s;
-    HC_CUDA(cudaMallocAsync(&dev.p, N * 8 * 9, s));       // 7 tables + out_len + status
-    u64 *d = (u64 *)dev.p;
-    u64 *d_out_len = d + 7 * N;
-    i32 *d_status = (i32 *)(d + 8 * N);
-    HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 5, cudaMemcpyHostToDevice, s));
-    HC_TRY(hc_compress_device(c, (const u8 *)c->in.p, d, d + N, d + 2 * N, nf, max_len, use_diff, use_adapt,
-                              (u8 *)c->out.p, d + 3 * N, d + 4 * N, d_out_len, d_status));
-    HC_CUDA(cudaMemcpyAsync(out_len, d_out_len, N * 8, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaMemcpyAsync(status, d_status, N * 4, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
-    // compact layout: files back to back, starts aligned to 16 bytes
-    u64 total = 0, max_out = 0;
-    for (u32 i = 0; i < nf; i++) {
-        u64 n = status[i] == 0 ? out_len[i] : 0;
-        if (status[i] != 0 && status[i] != HC_E_CAPACITY) out_len[i] = 0;
-        out_off[i] = total;
-        h[5 * N + i] = total;
-        h[6 * N + i] = n;
-        if (n > max_out) max_out = n;
-        total += align_up(n, 16);
+    // phase 2: in file order, turn the sizes of a finished group into compact offsets, gather its
+    // outputs on the device and start ONE device-to-host copy; later groups keep computing meanwhile
+    u64 total = 0;
+    for (u32 g = 0; g < ng; g++) {
+        hc_codec *k = c->kids[g];
+        GroupJob &j = jobs[g];
+        const u32 n = j.hi - j.lo;
+        const size_t N = n;
+        cudaStream_t s = k->stream;
+        HC_CUDA(cudaStreamSynchronize(s));
+        u64 *h = (u64 *)k->htab.p;
+        memcpy(out_len + j.lo, h + 7 * N, N * 8);
+        memcpy(status + j.lo, h + 8 * N, N * 4);
+        const u64 start = total;
+        u64 max_out = 0;
+        for (u32 i = 0; i < n; i++) {
+            const u32 f = j.lo + i;
+            const u64 len = status[f] == 0 ? out_len[f] : 0;
+            if (status[f] != 0 && status[f] != HC_E_CAPACITY) out_len[f] = 0;
+            out_off[f] = total;
+            h[5 * N + i] = total - start;
+            h[6 * N + i] = len;
+            if (len > max_out) max_out = len;
+            total += align_up(len, 16);
+        }
+        if (total > out_cap_total) {
+            for (u32 q = 0; q < ng; q++) cudaStreamSynchronize(c->kids[q]->stream);
+            return HC_E_CAPACITY;
+        }
+        const u64 gbytes = total - start;
+        HC_TRY(k->a.ensure((size_t)gbytes + 512));
+        u64 *d = j.d;
+        HC_CUDA(cudaMemcpyAsync(d + 5 * N, h + 5 * N, N * 8 * 2, cudaMemcpyHostToDevice, s));
+        HC_TRY(hc_gather_batch((const u8 *)k->out.p, d + 3 * N, d + 6 * N, (u8 *)k->a.p, d + 5 * N, n, max_out, s));
+        if (gbytes) HC_CUDA(cudaMemcpyAsync(out_base + start, k->a.p, (size_t)gbytes, cudaMemcpyDeviceToHost, s));
     }
-    if (total > out_cap_total) return HC_E_CAPACITY;
-    // gather strided -> compact on the device, then ONE device-to-host copy
-    HC_TRY(c->a.ensure((size_t)total + 512));
-    HC_CUDA(cudaMemcpyAsync(d + 5 * N, h + 5 * N, N * 8 * 2, cudaMemcpyHostToDevice, s));
-    HC_TRY(hc_gather_batch((const u8 *)c->out.p, d + 3 * N, d + 6 * N, (u8 *)c->a.p, d + 5 * N, nf, max_out, s));
-    if (total) HC_CUDA(cudaMemcpyAsync(out_base, c->a.p, (size_t)total, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
+    for (u32 g = 0; g < ng; g++) HC_CUDA(cudaStreamSynchronize(c->kids[g]->stream));
     return 0;
 }
 
@@ -779,60 +849,93 @@ extern "C" int hc_decompress_batch(hc_codec *c,
 {
     if (nf == 0) return 0;
     HC_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    std::vector<u64> d_off;
-    HC_TRY(upload_files(c, c->in, in_base, in_off, in_len, nf, d_off));
-    // header peek on the host: symbol counts size the FGK output, flag bytes select the kernels
-    u64 max_sym = 0;
-    int kinds = 0;
-    for (u32 i = 0; i < nf; i++) {
-        if (in_len[i] < 9) continue;
-        const u8 *p = in_base + in_off[i];
-        u64 m = 0;
-        for (int k = 0; k < 8; k++) m |= (u64)p[k] << (8 * k);
-        if (m > (in_len[i] - 9) * 8 + 1) m = 0;            // cannot decode: the kernel reports 9
-        if (m > max_sym) max_sym = m;
-        kinds |= (p[8] & 0x40) ? HC_KIND_ADAPT : HC_KIND_PLAIN;
-        if (p[8] & 0x80) kinds |= HC_KIND_DIFF;
+    const u32 ng = group_count(nf);
+    HC_TRY(ensure_kids(c, ng));
+    std::vector<GroupJob> jobs(ng);
+    // phase 1: upload, FGK decode and the size-only expansion pass of every group
+    for (u32 g = 0; g < ng; g++) {
+        hc_codec *k = c->kids[g];
+        GroupJob &j = jobs[g];
+        group_range(nf, g, ng, &j.lo, &j.hi);
+        const u32 n = j.hi - j.lo;
+        const size_t N = n;
+        cudaStream_t s = k->stream;
+        std::vector<u64> d_off;
+        HC_TRY(upload_files(k, k->in, in_base, in_off + j.lo, in_len + j.lo, n, d_off));
+        // header peek on the host: symbol counts size the FGK output, flag bytes select the kernels
+        u64 max_sym = 0;
+        int kinds = 0;
+        for (u32 i = 0; i < n; i++) {
+            const u64 len = in_len[j.lo + i];
+            if (len < 9) continue;
+            const u8 *p = in_base + in_off[j.lo + i];
+            u64 m = 0;
+            for (int b = 0; b < 8; b++) m |= (u64)p[b] << (8 * b);
+            if (m > (len - 9) * 8 + 1) m = 0;               // cannot decode: the kernel reports 9
+            if (m > max_sym) max_sym = m;
+            kinds |= (p[8] & 0x40) ? HC_KIND_ADAPT : HC_KIND_PLAIN;
+            if (p[8] & 0x80) kinds |= HC_KIND_DIFF;
+        }
+        if ((kinds & (HC_KIND_PLAIN | HC_KIND_ADAPT)) == 0) kinds |= HC_KIND_PLAIN;
+        j.kinds = kinds;
+        j.max_a = max_sym;
+        // pinned tables, 6 x n: in_off | in_len | out_off | out_cap | out_len (result) | status (result)
+        HC_TRY(k->htab.ensure(N * 8 * 6));
+        u64 *h = (u64 *)k->htab.p;
+        for (u32 i = 0; i < n; i++) { h[i] = d_off[i]; h[N + i] = in_len[j.lo + i]; }
+        j.dev.s = s;
+        HC_CUDA(cudaMallocAsync(&j.dev.p, N * 8 * 6, s));
+        j.d = (u64 *)j.dev.p;
+        u64 *d = j.d;
+        HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 2, cudaMemcpyHostToDevice, s));
+        stage_begin(k);
+        HC_TRY(dec_fgk(k, (const u8 *)k->in.p, d, d + N, n, max_sym));
+        HC_TRY(dec_expand(k, n, max_sym, 0, kinds, nullptr, nullptr, nullptr, d + 4 * N, (i32 *)(d + 5 * N)));
+        HC_CUDA(cudaMemcpyAsync(h + 4 * N, d + 4 * N, N * 8 * 2, cudaMemcpyDeviceToHost, s));   // pinned, see compress
     }
-    if ((kinds & (HC_KIND_PLAIN | HC_KIND_ADAPT)) == 0) kinds |= HC_KIND_PLAIN;
-    // pinned tables, 4 x nf: in_off | in_len | out_off | out_cap
-    HC_TRY(c->htab.ensure((size_t)nf * 8 * 4));
-    u64 *h = (u64 *)c->htab.p;
-    const size_t N = nf;
-    for (u32 i = 0; i < nf; i++) { h[i] = d_off[i]; h[N + i] = in_len[i]; }
-    AsyncFree dev;
-    dev.s = s;
-    HC_CUDA(cudaMallocAsync(&dev.p, N * 8 * 6, s));
-    u64 *d = (u64 *)dev.p;
-    u64 *d_out_len = d + 4 * N;
-    i32 *d_status = (i32 *)(d + 5 * N);
-    HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 2, cudaMemcpyHostToDevice, s));
-    // pass 1: FGK decode, then sizes only
-    stage_begin(c);
-    HC_TRY(dec_fgk(c, (const u8 *)c->in.p, d, d + N, nf, max_sym));
-    HC_TRY(dec_expand(c, nf, max_sym, 0, kinds, nullptr, nullptr, nullptr, d_out_len, d_status));
-    HC_CUDA(cudaMemcpyAsync(out_len, d_out_len, N * 8, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaMemcpyAsync(status, d_status, N * 4, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
-    u64 total = 0, max_out = 0;
-    for (u32 i = 0; i < nf; i++) {
-        u64 n = status[i] == 0 ? out_len[i] : 0;
-        out_off[i] = total;
-        h[2 * N + i] = total;
-        h[3 * N + i] = align_up(n, 16);
-        if (n > max_out) max_out = n;
-        total += align_up(n, 16);
+    // phase 2: in file order: offsets of the group, expansion straight into a compact buffer, copy out
+    u64 total = 0;
+    for (u32 g = 0; g < ng; g++) {
+        hc_codec *k = c->kids[g];
+        GroupJob &j = jobs[g];
+        const u32 n = j.hi - j.lo;
+        const size_t N = n;
+        cudaStream_t s = k->stream;
+        HC_CUDA(cudaStreamSynchronize(s));
+        u64 *h = (u64 *)k->htab.p;
+        memcpy(out_len + j.lo, h + 4 * N, N * 8);
+        memcpy(status + j.lo, h + 5 * N, N * 4);
+        const u64 start = total;
+        u64 max_out = 0;
+        for (u32 i = 0; i < n; i++) {
+            const u32 f = j.lo + i;
+            const u64 len = status[f] == 0 ? out_len[f] : 0;
+            out_off[f] = total;
+            h[2 * N + i] = total - start;
+            h[3 * N + i] = align_up(len, 16);
+            if (len > max_out) max_out = len;
+            total += align_up(len, 16);
+        }
+        if (total > out_cap_total) {
+            for (u32 q = 0; q < ng; q++) cudaStreamSynchronize(c->kids[q]->stream);
+            return HC_E_CAPACITY;
+        }
+        const u64 gbytes = total - start;
+        HC_TRY(k->out.ensure((size_t)gbytes + 512));
+        u64 *d = j.d;
+        HC_CUDA(cudaMemcpyAsync(d + 2 * N, h + 2 * N, N * 8 * 2, cudaMemcpyHostToDevice, s));
+        HC_TRY(dec_expand(k, n, j.max_a, max_out, j.kinds, (u8 *)k->out.p, d + 2 * N, d + 3 * N, d + 4 * N, (i32 *)(d + 5 * N)));
+        HC_CUDA(cudaMemcpyAsync(h + 4 * N, d + 4 * N, N * 8 * 2, cudaMemcpyDeviceToHost, s));
+        if (gbytes) HC_CUDA(cudaMemcpyAsync(out_base + start, k->out.p, (size_t)gbytes, cudaMemcpyDeviceToHost, s));
     }
-    if (total > out_cap_total) return HC_E_CAPACITY;
-    HC_TRY(c->out.ensure((size_t)total + 512));
-    HC_CUDA(cudaMemcpyAsync(d + 2 * N, h + 2 * N, N * 8 * 2, cudaMemcpyHostToDevice, s));
-    // pass 2: expansion straight into the compact layout (the FGK result of pass 1 is reused)
-    HC_TRY(dec_expand(c, nf, max_sym, max_out, kinds, (u8 *)c->out.p, d + 2 * N, d + 3 * N, d_out_len, d_status));
-    HC_CUDA(cudaMemcpyAsync(out_len, d_out_len, N * 8, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaMemcpyAsync(status, d_status, N * 4, cudaMemcpyDeviceToHost, s));
-    if (total) HC_CUDA(cudaMemcpyAsync(out_base, c->out.p, (size_t)total, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
+    for (u32 g = 0; g < ng; g++) {
+        hc_codec *k = c->kids[g];
+        HC_CUDA(cudaStreamSynchronize(k->stream));
+        const size_t N = jobs[g].hi - jobs[g].lo;
+        const u64 *h = (const u64 *)k->htab.p;
+        memcpy(out_len + jobs[g].lo, h + 4 * N, N * 8);
+        memcpy(status + jobs[g].lo, h + 5 * N, N * 4);
+    }
     for (u32 i = 0; i < nf; i++)
         if (status[i] != 0) out_len[i] = 0;
     return 0;

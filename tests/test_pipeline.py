@@ -218,3 +218,34 @@ def test_cli_matches_reference_cli(samples, golden):
                 assert r.stdout.decode() == c["stdout"]
             assert r.returncode == c["rc"], c
             assert r.stderr.decode() == c["stderr"].replace("$TMP", tmp), c
+
+
+def test_many_files_cross_group_pipeline(codec, oracle):
+    """> 128 files: the host-level calls split the batch into several group pipelines (own stream and
+    buffers each); offsets, lengths and statuses must still line up with the file order."""
+    cd, name = codec
+    rng = np.random.default_rng(5)
+    nfile = 200
+    files, widths = [], []
+    for i in range(nfile):
+        w = int(rng.integers(8, 24))
+        h = int(rng.integers(8, 20))
+        img = synth.image(("walk", "smooth", "random", "const")[i % 4], w, 1000 + i, h).reshape(-1)
+        if i % 37 == 5:
+            img = img[:-3]                     # size no longer a multiple of the width -> status 6
+        files.append(img)
+        widths.append(w)
+    outs, st = cd.compress(files, diff=True, adapt=True, width=widths)
+    good = []
+    for i, (f, w, o) in enumerate(zip(files, widths, outs)):
+        rc, exp = oracle.compress(f, diff=True, adapt=True, width=w)
+        assert st[i] == rc, i
+        if rc == 0:
+            assert np.array_equal(o, exp), i
+            good.append(i)
+        else:
+            assert o.size == 0
+    back, st2 = cd.decompress([outs[i] for i in good])
+    assert not st2.any()
+    for i, b in zip(good, back):
+        assert np.array_equal(b, files[i]), i
