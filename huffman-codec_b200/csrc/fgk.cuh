@@ -162,18 +162,29 @@ HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, b
     if (a != c.root) {
         uint2 n = lds64(a);
         u32 w1 = lds32(a + 8u);
+        // two levels per iteration so that the prefetched entry (pn / n) alternates between two
+        // register sets instead of being copied every level
         for (;;) {
-            u32 parent = n.y;
-            uint2 pn = lds64(parent);
-            u32 pw1 = lds32(parent + 8u);
-            if (w1 == n.x && fgk_leader_swap(c, a, parent, n.x, lane, watch, moved)) {
-                pn = lds64(parent);
-                pw1 = lds32(parent + 8u);
+            u32 p = n.y;                                   // level A: node a, entry n
+            uint2 pn = lds64(p);
+            u32 pw1 = lds32(p + 8u);
+            if (w1 == n.x && fgk_leader_swap(c, a, p, n.x, lane, watch, moved)) {
+                pn = lds64(p);
+                pw1 = lds32(p + 8u);
             }
             FGK_LEVEL_SYNC();
             sts32_if(w0, a, n.x + 1u);
-            if (parent == c.root) break;
-            a = parent; n = pn; w1 = pw1;
+            if (p == c.root) break;
+            a = pn.y;                                      // level B: node p, entry pn
+            n = lds64(a);
+            w1 = lds32(a + 8u);
+            if (pw1 == pn.x && fgk_leader_swap(c, p, a, pn.x, lane, watch, moved)) {
+                n = lds64(a);
+                w1 = lds32(a + 8u);
+            }
+            FGK_LEVEL_SYNC();
+            sts32_if(w0, p, pn.x + 1u);
+            if (a == c.root) break;
         }
     }
     sts32_if(w0, c.root, count);
@@ -189,28 +200,48 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
     const bool w0 = lane == 0;
     uint2 n = lds64(a);                       // a is a leaf: never the root
     u32 w1 = lds32(a + 8u);
+    // two levels per iteration (register sets alternate, see fgk_update_plain)
     for (;;) {
-        u32 parent = n.y;
-        uint2 pn = lds64(parent);
-        u32 pw1 = lds32(parent + 8u);
+        u32 p = n.y;                                       // level A: node a, entry n
+        uint2 pn = lds64(p);
+        u32 pw1 = lds32(p + 8u);
         fgk_code_bit(a, hi, lo);
         if (w1 == n.x) {
-            const u32 old_parent = parent;
-            if (fgk_leader_swap(c, a, parent, n.x, lane, watch, moved)) {
-                if (old_parent != c.root) {   // pn still holds the old parent's entry
+            const u32 old_parent = p;
+            if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved)) {
+                if (old_parent != c.root) {                // pn still holds the old parent's entry
                     fgk_code_bit(old_parent, hi, lo);
-                    for (u32 p = pn.y; p != c.root; p = lds32(p + 4u)) fgk_code_bit(p, hi, lo);
+                    for (u32 q = pn.y; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
                 }
                 FGK_LEVEL_SYNC();
                 sts32_if(w0, a, n.x + 1u);
-                fgk_update_plain(c, parent, lane, count, watch, moved);
+                fgk_update_plain(c, p, lane, count, watch, moved);
                 return;
             }
         }
         FGK_LEVEL_SYNC();
         sts32_if(w0, a, n.x + 1u);
-        if (parent == c.root) break;
-        a = parent; n = pn; w1 = pw1;
+        if (p == c.root) break;
+        a = pn.y;                                          // level B: node p, entry pn
+        n = lds64(a);
+        w1 = lds32(a + 8u);
+        fgk_code_bit(p, hi, lo);
+        if (pw1 == pn.x) {
+            const u32 old_parent = a;
+            if (fgk_leader_swap(c, p, a, pn.x, lane, watch, moved)) {
+                if (old_parent != c.root) {                // n still holds the old parent's entry
+                    fgk_code_bit(old_parent, hi, lo);
+                    for (u32 q = n.y; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
+                }
+                FGK_LEVEL_SYNC();
+                sts32_if(w0, p, pn.x + 1u);
+                fgk_update_plain(c, a, lane, count, watch, moved);
+                return;
+            }
+        }
+        FGK_LEVEL_SYNC();
+        sts32_if(w0, p, pn.x + 1u);
+        if (a == c.root) break;
     }
     sts32_if(w0, c.root, count);
     syncwarp();
@@ -442,25 +473,41 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
         // walk down on a private copy of the window's top 32 bits, consume them afterwards.  Lane j
         // remembers the node reached after j+1 steps: the walk visits exactly the nodes the update
         // will increment, so the update needs no second (leaf->root) chase.
-        u32 d = root_down, k = lds32(d), t = (u32)(br.win >> 32), len = 0, depth = 0, dk = 0;
+        u32 d = root_down, k = lds32(d), t = (u32)(br.win >> 32), depth = 0, dk = 0;
+        // fast walk: no length check inside the loop.  Past 32 steps `t` only supplies zeros, i.e. the
+        // walk keeps taking (valid) left children and still ends at a leaf; such a symbol is redone below.
         while (!(k & 1u)) {
-            if (len == 32u) {                            // code longer than 32 bits (very deep tree)
-                if (br.avail < 32u) { err = 9; break; }
-                br_skip(br, 32, lane);
-                t = (u32)(br.win >> 32);
-                len = 0;
-            }
-            d = k + ((t >> 31) << 2);
+            d = k + ((t >> 29) & 4u);
             if (lane == depth) dk = d;
             t <<= 1;
-            len++;
             depth++;
             k = lds32(d);
         }
-        if (err) break;
-        if (len) {
-            if (br.avail < len) { err = 9; break; }      // ran out of bits inside a code
-            br_skip(br, len, lane);
+        if (depth > 32u) {
+            // code longer than 32 bits (very deep tree): exact walk, 32 bits at a time
+            d = root_down; k = lds32(d); t = (u32)(br.win >> 32); depth = 0;
+            u32 len = 0;
+            while (!(k & 1u)) {
+                if (len == 32u) {
+                    if (br.avail < 32u) { err = 9; break; }
+                    br_skip(br, 32, lane);
+                    t = (u32)(br.win >> 32);
+                    len = 0;
+                }
+                d = k + ((t >> 29) & 4u);
+                t <<= 1;
+                len++;
+                depth++;
+                k = lds32(d);
+            }
+            if (err) break;
+            if (len) {
+                if (br.avail < len) { err = 9; break; }
+                br_skip(br, len, lane);
+            }
+        } else if (depth) {
+            if (br.avail < depth) { err = 9; break; }    // ran out of bits inside a code
+            br_skip(br, depth, lane);
         }
         count++;
         u32 y;
