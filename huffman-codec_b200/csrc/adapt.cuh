@@ -129,7 +129,8 @@ constexpr int AD_COST_TPB = 256;
 
 HC_KERNEL HC_LAUNCH_BOUNDS(AD_COST_TPB, 4)
 adapt_cost_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT width,
-                  const u64 *HC_RESTRICT height, u32 nf, u32 *HC_RESTRICT cost, u64 cost_stride, u32 nchunks)
+                  const u64 *HC_RESTRICT height, u32 nf, u32 *HC_RESTRICT cost, u64 cost_stride, u32 nchunks,
+                  u64 skip_w, u64 skip_h)
 {
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const int k = (int)(blockIdx.x % AD_NCAND);
@@ -139,6 +140,7 @@ adapt_cost_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
         const u64 w = width[f], h = height[f];
         if (w < 8 || h < 8 || !ad_cand_valid(w, h, k)) continue;
+        if (w <= skip_w && h <= skip_h) continue;          // handled by adapt_cost_mask_kernel
         const u8 *mat = in + in_off[f];
         u32 *tab = cost + (u64)f * cost_stride + ad_kbase(w, h, k);
         const u64 nb = ad_nblocks(w, h, b);

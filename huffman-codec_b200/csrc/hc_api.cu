@@ -21,6 +21,7 @@
 #include "diff.cuh"
 #include "rle.cuh"
 #include "adapt.cuh"
+#include "adapt_mask.cuh"
 #include "fgk.cuh"
 
 static std::atomic<uint64_t> g_launches{0};
@@ -299,8 +300,20 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
     u64 want = (592 * 2 + (u64)nf * AD_NCAND - 1) / ((u64)nf * AD_NCAND);
     if (chunks > want) chunks = want < 1 ? 1 : want;
     if (chunks > 4096) chunks = 4096;
+    // matrices up to 512 x 512: search from equality bitmasks in shared memory (adapt_mask.cuh);
+    // larger ones: generic per-block evaluation
+#ifndef HC_EMU
+    static bool smem_attr_set = false;
+    if (!smem_attr_set) {
+        HC_CUDA(cudaFuncSetAttribute(adapt_cost_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACM_SMEM));
+        smem_attr_set = true;
+    }
+#endif
+    HC_LAUNCH(adapt_cost_mask_kernel, dim3(nf < 1184u ? nf : 1184u), dim3(ACM_TPB), ACM_SMEM, stream, in, in_off, width, height,
+              nf, cost, cs);
+    HC_CHECK_LAUNCH();
     HC_LAUNCH(adapt_cost_kernel, grid2(chunks * AD_NCAND, nf), dim3(AD_COST_TPB), 0, stream, in, in_off, width,
-              height, nf, cost, cs, (u32)chunks);
+              height, nf, cost, cs, (u32)chunks, (u64)ACM_MAX, (u64)ACM_MAX);
     HC_CHECK_LAUNCH();
     HC_LAUNCH(adapt_select_kernel, dim3(file_grid(nf)), dim3(256), 0, stream, width, height, nf,
               (const u32 *)cost, cs, boff, os, out, out_off, out_len, cb, status);

@@ -159,6 +159,13 @@ def _adapt_inputs(be):
     for i, (w, h) in enumerate(shapes):
         for k in (kinds[i % 5], kinds[(i + 2) % 5]):
             imgs.append((w, h, synth.image(k, w, 50 + i, h).reshape(-1)))
+    # large-block paths of the mask search (B >= 64: one warp per block; flat areas: long-run correction)
+    for i, (w, h, k) in enumerate(((192, 128, "const"), (128, 192, "longrun"), (136, 200, "smooth"), (128, 128, "walk"))):
+        imgs.append((w, h, synth.image(k, w, 90 + i, h).reshape(-1)))
+    big = np.zeros((160, 192), np.uint8)
+    big[:, 100:] = 7                       # two flat halves: runs of >= 258 in both scan directions
+    big[70:, :] += 3
+    imgs.append((192, 160, big.reshape(-1)))
     # gradients that favour vertical / horizontal scanning
     y, x = np.mgrid[0:64, 0:64]
     imgs.append((64, 64, (x & 255).astype(np.uint8).reshape(-1)))
