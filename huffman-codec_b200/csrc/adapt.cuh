@@ -62,6 +62,18 @@ HC_HD u32 ad_lanes(u64 b)
     return l;
 }
 
+// eligibility of a file for the small-block kernels (adapt_small.cuh); same formula as
+// ads_rows_per_group, declared here because the lane-group kernels must skip those files
+HC_HD u32 ads_rows_per_group_fwd(u64 w, u64 b)
+{
+    if (b > 32 || b * w > 32 * 1024) return 0;
+    const u64 ncb = (w + b - 1) / b;
+    u64 s = 256 / ncb;
+    const u64 cap = (32 * 1024) / (b * w);
+    if (s > cap) s = cap;
+    return (u32)s;
+}
+
 // sequential reader of a block in horizontal (row-major) or vertical (column-major) order
 struct BlockCursor {
     const u8 *p;       // matrix + block base
@@ -259,12 +271,13 @@ HC_KERNEL HC_LAUNCH_BOUNDS(AD_EMIT_TPB, 4)
 adapt_emit_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT width,
                   const u64 *HC_RESTRICT height, u32 nf, const u32 *HC_RESTRICT cost, u64 cost_stride,
                   const u32 *HC_RESTRICT blk_off, u64 off_stride, const u64 *HC_RESTRICT chosen_b,
-                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status)
+                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, bool skip_small)
 {
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
         if (status[f] != 0) continue;
         const u64 w = width[f], h = height[f], b = chosen_b[f];
+        if (skip_small && ads_rows_per_group_fwd(w, b)) continue;     // adapt_emit_small_kernel
         int k = 0;
         while ((8ull << k) < b) k++;
         const u32 L = ad_lanes(b), G = 32u / L, gl = lane % L, gi = lane / L;
@@ -477,7 +490,7 @@ constexpr int AD_EXP_TPB = 256;
 HC_KERNEL HC_LAUNCH_BOUNDS(AD_EXP_TPB, 4)
 adapt_expand_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                     const u32 *HC_RESTRICT blk_start, u64 blk_stride, u8 *HC_RESTRICT out,
-                    const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, u32 nf)
+                    const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, u32 nf, bool skip_small)
 {
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
@@ -485,6 +498,7 @@ adapt_expand_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, con
         const u8 *src = in + in_off[f];
         const AdaptHeader hd = ad_parse_header(src, in_len[f]);
         if (hd.nb == 0) continue;
+        if (skip_small && hd.w <= 0xffffffffull && hd.h <= 0xffffffffull && ads_rows_per_group_fwd(hd.w, hd.b)) continue;
         const u32 *tab = blk_start + (u64)f * blk_stride;
         u8 *mat = out + out_off[f];
         const u32 L = ad_lanes(hd.b), G = 32u / L, gl = lane % L, gi = lane / L;

@@ -22,6 +22,7 @@
 #include "rle.cuh"
 #include "adapt.cuh"
 #include "adapt_mask.cuh"
+#include "adapt_small.cuh"
 #include "fgk.cuh"
 
 static std::atomic<uint64_t> g_launches{0};
@@ -323,8 +324,23 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
     u64 ewant = (592 * 2 + nf - 1) / nf;
     if (echunks > ewant) echunks = ewant;
     HC_LAUNCH(adapt_emit_kernel, grid2(echunks, nf), dim3(AD_EMIT_TPB), 0, stream, in, in_off, width, height, nf,
-              (const u32 *)cost, cs, (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status);
+              (const u32 *)cost, cs, (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status, true);
     HC_CHECK_LAUNCH();
+    // files whose winning block size is 8/16/32: one thread per block over shared-memory staged rows
+#ifndef HC_EMU
+    static bool emit_attr_set = false;
+    if (!emit_attr_set) {
+        HC_CUDA(cudaFuncSetAttribute(adapt_emit_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADS_SMEM));
+        emit_attr_set = true;
+    }
+#endif
+    {
+        u64 gx = max_len / ADS_STRIP + 1;
+        if (gx > 64) gx = 64;
+        HC_LAUNCH(adapt_emit_small_kernel, grid2(gx, nf), dim3(ADS_TPB), ADS_SMEM, stream, in, in_off, width, height, nf,
+                  (const u32 *)cost, cs, (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status);
+        HC_CHECK_LAUNCH();
+    }
     if (chosen_b)
         HC_CUDA(cudaMemcpyAsync(chosen_b, cb, (size_t)nf * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
@@ -362,8 +378,22 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
     u64 want = (592 * 2 + nf - 1) / nf;
     if (chunks > want) chunks = want;
     HC_LAUNCH(adapt_expand_kernel, grid2(chunks, nf), dim3(AD_EXP_TPB), 0, stream, in, in_off, in_len, (const u32 *)ws, bs,
-              out, out_off, (const i32 *)status, nf);
+              out, out_off, (const i32 *)status, nf, true);
     HC_CHECK_LAUNCH();
+#ifndef HC_EMU
+    static bool exp_attr_set = false;
+    if (!exp_attr_set) {
+        HC_CUDA(cudaFuncSetAttribute(adapt_expand_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADS_SMEM));
+        exp_attr_set = true;
+    }
+#endif
+    {
+        u64 gx = max_out_len / ADS_STRIP + 1;
+        if (gx > 64) gx = 64;
+        HC_LAUNCH(adapt_expand_small_kernel, grid2(gx, nf), dim3(ADS_TPB), ADS_SMEM, stream, in, in_off, in_len, (const u32 *)ws, bs,
+                  out, out_off, (const i32 *)status, nf);
+        HC_CHECK_LAUNCH();
+    }
     // headers with more blocks than the table holds (block size < 8) take the serial decoder
     HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off, out_cap,
               out_len, status, nf, (i32)AD_ST_SERIAL);
