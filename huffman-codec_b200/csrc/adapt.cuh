@@ -74,6 +74,15 @@ HC_HD u32 ads_rows_per_group_fwd(u64 w, u64 b)
     return (u32)s;
 }
 
+// eligibility of a file for the large-block kernels (adapt_large.cuh): one CTA per block through
+// the streaming coder of rle.cuh
+constexpr u64 ADL_MINB = 64;
+constexpr u64 ADL_MAXB = 4096;                 // bw*bh fits 32 bits with room
+HC_HD bool adl_eligible(u64 w, u64 h, u64 b)
+{
+    return b >= ADL_MINB && b <= ADL_MAXB && (b & 15u) == 0 && w <= 0x7fffffffull && h <= 0x7fffffffull && w >= 1 && h >= 1;
+}
+
 // sequential reader of a block in horizontal (row-major) or vertical (column-major) order
 struct BlockCursor {
     const u8 *p;       // matrix + block base
@@ -271,13 +280,15 @@ HC_KERNEL HC_LAUNCH_BOUNDS(AD_EMIT_TPB, 4)
 adapt_emit_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT width,
                   const u64 *HC_RESTRICT height, u32 nf, const u32 *HC_RESTRICT cost, u64 cost_stride,
                   const u32 *HC_RESTRICT blk_off, u64 off_stride, const u64 *HC_RESTRICT chosen_b,
-                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, bool skip_small)
+                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, bool skip_small,
+                  u64 large_max)
 {
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
         if (status[f] != 0) continue;
         const u64 w = width[f], h = height[f], b = chosen_b[f];
         if (skip_small && ads_rows_per_group_fwd(w, b)) continue;     // adapt_emit_small_kernel
+        if (adl_eligible(w, h, b) && w * h <= large_max) continue;    // adapt_emit_large_kernel
         int k = 0;
         while ((8ull << k) < b) k++;
         const u32 L = ad_lanes(b), G = 32u / L, gl = lane % L, gi = lane / L;
@@ -490,7 +501,8 @@ constexpr int AD_EXP_TPB = 256;
 HC_KERNEL HC_LAUNCH_BOUNDS(AD_EXP_TPB, 4)
 adapt_expand_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                     const u32 *HC_RESTRICT blk_start, u64 blk_stride, u8 *HC_RESTRICT out,
-                    const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, u32 nf, bool skip_small)
+                    const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status, u32 nf, bool skip_small,
+                    u64 large_max)
 {
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
@@ -499,6 +511,7 @@ adapt_expand_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, con
         const AdaptHeader hd = ad_parse_header(src, in_len[f]);
         if (hd.nb == 0) continue;
         if (skip_small && hd.w <= 0xffffffffull && hd.h <= 0xffffffffull && ads_rows_per_group_fwd(hd.w, hd.b)) continue;
+        if (adl_eligible(hd.w, hd.h, hd.b) && hd.total <= large_max) continue;   // adapt_expand_large_kernel
         const u32 *tab = blk_start + (u64)f * blk_stride;
         u8 *mat = out + out_off[f];
         const u32 L = ad_lanes(hd.b), G = 32u / L, gl = lane % L, gi = lane / L;

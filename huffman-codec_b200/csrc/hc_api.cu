@@ -23,6 +23,7 @@
 #include "adapt.cuh"
 #include "adapt_mask.cuh"
 #include "adapt_small.cuh"
+#include "adapt_large.cuh"
 #include "fgk.cuh"
 
 static std::atomic<uint64_t> g_launches{0};
@@ -275,13 +276,15 @@ extern "C" int hc_rle_decode_batch(const uint8_t *in, const uint64_t *in_off, co
     return 0;
 }
 
-// scratch layout of the adaptive encoder (per file): cost table | block offsets ; then chosen_b
+// scratch layout of the adaptive encoder: block streams of the large-block path (per file) | cost
+// tables | block offsets | chosen_b
 static inline u64 ad_cost_stride(u64 max_len) { return max_len / 16 + 32; }
 static inline u64 ad_off_stride(u64 max_len) { return max_len / 32 + 16; }
+static inline u64 ad_large_bytes(u32 nf, u64 max_len) { return max_len >= ADL_MINB * ADL_MINB ? (u64)nf * adl_tmp_stride(max_len) : 0; }
 
 extern "C" uint64_t hc_adapt_encode_ws_bytes(uint32_t nf, uint64_t max_len)
 {
-    return (uint64_t)nf * ((ad_cost_stride(max_len) + ad_off_stride(max_len)) * 4 + 8) + 256;
+    return ad_large_bytes(nf, max_len) + (uint64_t)nf * ((ad_cost_stride(max_len) + ad_off_stride(max_len)) * 4 + 8) + 256;
 }
 
 extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
@@ -292,7 +295,9 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
 {
     if (nf == 0) return 0;
     const u64 cs = ad_cost_stride(max_len), os = ad_off_stride(max_len);
-    u32 *cost = (u32 *)ws;
+    const u64 lbytes = ad_large_bytes(nf, max_len), tstride = lbytes ? adl_tmp_stride(max_len) : 0;
+    u8 *ltmp = (u8 *)ws;
+    u32 *cost = (u32 *)((u8 *)ws + lbytes);
     u32 *boff = cost + (u64)nf * cs;
     u64 *cb = (u64 *)(((uintptr_t)(boff + (u64)nf * os) + 7) & ~(uintptr_t)7);
     // work split: enough CTAs to fill 148 SMs, at most one chunk per 64 KiB of image
@@ -324,8 +329,21 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
     u64 ewant = (592 * 2 + nf - 1) / nf;
     if (echunks > ewant) echunks = ewant;
     HC_LAUNCH(adapt_emit_kernel, grid2(echunks, nf), dim3(AD_EMIT_TPB), 0, stream, in, in_off, width, height, nf,
-              (const u32 *)cost, cs, (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status, true);
+              (const u32 *)cost, cs, (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status, true, tstride);
     HC_CHECK_LAUNCH();
+    // files whose winning block size is >= 64: one CTA per block through the streaming coder
+    if (lbytes) {
+        u64 gx = max_len / (ADL_T * ADL_T) + 1;
+        if (gx > 64) gx = 64;
+        HC_LAUNCH(adapt_gather_large_kernel, grid2(gx, nf), dim3(ADL_TPB), 0, stream, in, in_off, width, height, nf,
+                  (const u32 *)cost, cs, (const u64 *)cb, (const i32 *)status, ltmp, tstride);
+        HC_CHECK_LAUNCH();
+        u64 gb = max_len / (ADL_MINB * ADL_MINB) + 1;
+        if (gb > 16) gb = 16;
+        HC_LAUNCH(adapt_emit_large_kernel, grid2(gb, nf), dim3(TPB), 0, stream, (const u8 *)ltmp, tstride, width, height, nf,
+                  (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status);
+        HC_CHECK_LAUNCH();
+    }
     // files whose winning block size is 8/16/32: one thread per block over shared-memory staged rows
 #ifndef HC_EMU
     static bool emit_attr_set = false;
@@ -350,7 +368,8 @@ static inline u64 ad_blk_stride(u64 max_out_len) { return max_out_len / 32 + 16;
 
 extern "C" uint64_t hc_adapt_decode_ws_bytes(uint32_t nf, uint64_t max_out_len)
 {
-    return (uint64_t)nf * ad_blk_stride(max_out_len) * 4 + 256;   // block start table
+    // block streams of the large-block path | block start table
+    return ad_large_bytes(nf, max_out_len) + (uint64_t)nf * ad_blk_stride(max_out_len) * 4 + 256;
 }
 
 extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
@@ -369,6 +388,9 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
         return 0;
     }
     const u64 bs = ad_blk_stride(max_out_len);
+    const u64 lbytes = ad_large_bytes(nf, max_out_len), tstride = lbytes ? adl_tmp_stride(max_out_len) : 0;
+    u8 *ltmp = (u8 *)ws;
+    ws = ws ? (void *)((u8 *)ws + lbytes) : ws;
     HC_LAUNCH(adapt_index_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out_cap, out != nullptr,
               (u32 *)ws, bs, out_len, status, nf);
     HC_CHECK_LAUNCH();
@@ -378,8 +400,20 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
     u64 want = (592 * 2 + nf - 1) / nf;
     if (chunks > want) chunks = want;
     HC_LAUNCH(adapt_expand_kernel, grid2(chunks, nf), dim3(AD_EXP_TPB), 0, stream, in, in_off, in_len, (const u32 *)ws, bs,
-              out, out_off, (const i32 *)status, nf, true);
+              out, out_off, (const i32 *)status, nf, true, tstride);
     HC_CHECK_LAUNCH();
+    if (lbytes) {
+        u64 gb = max_out_len / (ADL_MINB * ADL_MINB) + 1;
+        if (gb > 16) gb = 16;
+        HC_LAUNCH(adapt_expand_large_kernel, grid2(gb, nf), dim3(TPB), 0, stream, in, in_off, in_len, (const u32 *)ws, bs,
+                  (const i32 *)status, nf, ltmp, tstride);
+        HC_CHECK_LAUNCH();
+        u64 gx = max_out_len / (ADL_T * ADL_T) + 1;
+        if (gx > 64) gx = 64;
+        HC_LAUNCH(adapt_scatter_large_kernel, grid2(gx, nf), dim3(ADL_TPB), 0, stream, in, in_off, in_len,
+                  (const i32 *)status, nf, (const u8 *)ltmp, tstride, out, out_off);
+        HC_CHECK_LAUNCH();
+    }
 #ifndef HC_EMU
     static bool exp_attr_set = false;
     if (!exp_attr_set) {

@@ -128,9 +128,9 @@ HC_DEV void sw_finish(StageWriter &w)
     for (u32 i = w.skip; i < w.fill; i++) sts8(w.waddr + i, word >> (8u * i));
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
-rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
-                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u64 *HC_RESTRICT out_len, u32 nf)
+// Encodes the n-byte stream at src (16-byte aligned) to dst (any alignment); called by all TPB
+// threads of a CTA, returns the number of bytes written.  Ends with a CTA barrier.
+HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT dst)
 {
     HC_SHARED u32 wtot[2][32];
     HC_SHARED u32 s_carry_run;
@@ -138,11 +138,9 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     HC_SMEM_ARENA(wtot);
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 stage = smem_addr(sout);
-
-    for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
-        const u64 n = in_len[f];
-        const u8 *src = in + in_off[f];
-        u8 *dst = out + out_off[f];
+    const u32 dphase = (u32)((uintptr_t)dst & 15u);
+    {
+        {
         u64 out_pos = 0;      // bytes emitted by all previous tiles
         u32 carry_run = 0;    // length of the run that ends at the last element of the previous tile
 
@@ -217,7 +215,7 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
 
             // ---- stage the output bytes -------------------------------------------------
-            const u32 shift = (u32)(out_pos & 15u);
+            const u32 shift = (u32)((dphase + out_pos) & 15u);
 #pragma unroll
             for (int j = 0; j < UN; j++) {
                 if (cnt[j] == 0) continue;
@@ -254,7 +252,7 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             carry_run = s_carry_run;
             // ---- copy out: sout[shift .. shift+total) -> dst[out_pos ..) ---------------------
             {
-                u8 *gbase = dst + (out_pos - shift);            // 16-byte aligned
+                u8 *gbase = dst + out_pos - shift;              // 16-byte aligned
                 const u32 end = shift + total;
                 const u32 nchunk = (end + 15u) / 16u;
                 for (u32 c = tid; c < nchunk; c += TPB) {
@@ -272,8 +270,18 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             for (int j = 0; j < UN; j++) cur[j] = nxt[j];
             syncthreads();
         }
-        if (tid == 0) out_len[f] = out_pos;
-        syncthreads();
+        return out_pos;
+        }
+    }
+}
+
+HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
+rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
+                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u64 *HC_RESTRICT out_len, u32 nf)
+{
+    for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
+        const u64 m = rle_encode_stream(in + in_off[f], in_len[f], out + out_off[f]);
+        if (threadIdx.x == 0) out_len[f] = m;
     }
 }
 
@@ -296,22 +304,22 @@ struct OpCompose { HC_DEVM u32 operator()(u32 a, u32 b) const { return map_compo
 
 constexpr u32 DEC_WIN = TPB * 64;   // 16 KiB of output per expansion window
 
-HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
-rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
-                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
-                  u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
+// Decodes the n0-byte token stream at src0 (any alignment) to dst (16-byte aligned, or null to
+// only measure), writing at most cap bytes; called by all TPB threads of a CTA, returns the decoded
+// length.  An unaligned stream is read from the 16-byte boundary below it with the leading bytes
+// masked out (they belong to the caller's buffer: a header or the previous block's tokens).
+HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT dst, u64 cap)
 {
     HC_SHARED u32 wtot[2][32];
     HC_SHARED u32 wlast[NW];
     HC_SHARED u32 heads[DEC_WIN / 32];
     HC_SHARED HC_ALIGNED16 u8 sval[DEC_WIN];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
-    for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
-        const u64 n = in_len[f];
-        const u8 *src = in + in_off[f];
-        u8 *dst = out ? out + out_off[f] : (u8 *)0;
-        const u64 cap = out ? out_cap[f] : 0;
+    const u32 lead = n0 ? (u32)((uintptr_t)src0 & 15u) : 0u;
+    const u8 *src = src0 - lead;
+    const u64 n = n0 + lead;
+    {
+        {
         u64 out_pos = 0;
         u32 carry_state = 0;
 
@@ -337,6 +345,7 @@ rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                 if (lane == 0) pb = (p > 0 && p < n) ? ldg8(src + p - 1) : 0u;
                 pbyte[j] = pb;
                 u32 vm = p >= n ? 0u : (n - p >= 16 ? 0xffffu : ((1u << (u32)(n - p)) - 1u));
+                if (p == 0) vm &= ~((1u << lead) - 1u);
                 u32 e = 0, prev = pb, m = MAP_ID;
 #pragma unroll
                 for (int k = 0; k < 16; k++) {
@@ -457,11 +466,23 @@ rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             for (int j = 0; j < UN; j++) cur[j] = nxt[j];
             syncthreads();
         }
-        if (tid == 0) {
-            out_len[f] = out_pos;
-            if (status) status[f] = (out && out_pos > cap) ? 100 : 0;
+        return out_pos;
         }
-        syncthreads();
+    }
+}
+
+HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
+rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
+                  u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
+                  u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
+{
+    for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
+        const u64 cap = out ? out_cap[f] : 0;
+        const u64 m = rle_decode_stream(in + in_off[f], in_len[f], out ? out + out_off[f] : (u8 *)0, cap);
+        if (threadIdx.x == 0) {
+            out_len[f] = m;
+            if (status) status[f] = (out && m > cap) ? 100 : 0;
+        }
     }
 }
 

@@ -160,7 +160,10 @@ def _adapt_inputs(be):
         for k in (kinds[i % 5], kinds[(i + 2) % 5]):
             imgs.append((w, h, synth.image(k, w, 50 + i, h).reshape(-1)))
     # large-block paths of the mask search (B >= 64: one warp per block; flat areas: long-run correction)
-    for i, (w, h, k) in enumerate(((192, 128, "const"), (128, 192, "longrun"), (136, 200, "smooth"), (128, 128, "walk"))):
+    # and of adapt_large.cuh (one CTA per block, ragged edge blocks in both directions)
+    for i, (w, h, k) in enumerate(((192, 128, "const"), (128, 192, "longrun"), (136, 200, "smooth"), (128, 128, "walk"),
+                                   (200, 136, "random"), (333, 100, "random"), (136, 200, "const"), (70, 130, "const"),
+                                   (97, 151, "longrun"))):
         imgs.append((w, h, synth.image(k, w, 90 + i, h).reshape(-1)))
     big = np.zeros((160, 192), np.uint8)
     big[:, 100:] = 7                       # two flat halves: runs of >= 258 in both scan directions
@@ -170,6 +173,9 @@ def _adapt_inputs(be):
     y, x = np.mgrid[0:64, 0:64]
     imgs.append((64, 64, (x & 255).astype(np.uint8).reshape(-1)))
     imgs.append((64, 64, (y & 255).astype(np.uint8).reshape(-1)))
+    y, x = np.mgrid[0:136, 0:200]          # ragged large blocks, vertical and horizontal winners
+    imgs.append((200, 136, ((x * 7) & 255).astype(np.uint8).reshape(-1)))
+    imgs.append((200, 136, ((y * 7) & 255).astype(np.uint8).reshape(-1)))
     return imgs
 
 
@@ -217,6 +223,13 @@ def test_adapt_decode(be, oracle):
     for (w, h, im) in imgs[:6]:
         encs.append(oracle.adapt_encode_bs(im, w, h, 8))
         imgs = imgs + [(w, h, im)]
+    # forced large block sizes on ragged shapes: multiples of 64 (adapt_large.cuh), a multiple of 16
+    # only (strips with a remainder) and one that is neither (lane-group kernel)
+    for (w, h, kind) in ((130, 70, "walk"), (200, 136, "smooth"), (100, 333, "longrun")):
+        im = synth.image(kind, w, 7, h).reshape(-1)
+        for bsz in (64, 128, 80, 72):
+            encs.append(oracle.adapt_encode_bs(im, w, h, bsz))
+            imgs = imgs + [(w, h, im)]
     # a stream with block size 4 (never produced by the reference encoder, accepted by its decoder)
     img4 = synth.image("walk", 12, 77, 8).reshape(-1)
     encs.append(oracle.adapt_encode_bs(img4, 12, 8, 4))
