@@ -126,6 +126,7 @@ adapt_emit_large_kernel(const u8 *HC_RESTRICT tmp, u64 tstride, const u64 *HC_RE
                         u32 nf, const u32 *HC_RESTRICT blk_off, u64 off_stride, const u64 *HC_RESTRICT chosen_b,
                         u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status)
 {
+    rle_enc_init();
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
         if (status[f] != 0) continue;
         const u64 w = width[f], h = height[f], b = chosen_b[f];

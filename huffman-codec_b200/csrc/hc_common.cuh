@@ -98,6 +98,14 @@ HC_DEV int clzll(u64 v) { return v ? __builtin_clzll(v) : 64; }
 HC_DEV int ffs(u32 v) { return __builtin_ffs((int)v); }
 HC_DEV int ffsll(u64 v) { return __builtin_ffsll((long long)v); }
 HC_DEV u32 bswap32(u32 v) { return __builtin_bswap32(v); }
+// PRMT in its default mode: result byte i = byte (sel nibble i) of the 8 bytes {b:a}
+HC_DEV u32 prmt(u32 a, u32 b, u32 sel)
+{
+    const u64 src = ((u64)b << 32) | a;
+    u32 r = 0;
+    for (int i = 0; i < 4; i++) r |= (u32)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 HC_DEV u32 brev(u32 v) { u32 r = 0; for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i); return r; }
 HC_DEV u64 bswap64(u64 v) { return __builtin_bswap64(v); }
 HC_DEV u32 vadd4(u32 a, u32 b)
@@ -166,6 +174,7 @@ HC_DEV int clzll(u64 v) { return __clzll((long long)v); }
 HC_DEV int ffs(u32 v) { return __ffs((int)v); }
 HC_DEV int ffsll(u64 v) { return __ffsll((long long)v); }
 HC_DEV u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
+HC_DEV u32 prmt(u32 a, u32 b, u32 sel) { return __byte_perm(a, b, sel); }
 HC_DEV u32 brev(u32 v) { return __brev(v); }
 HC_DEV u64 bswap64(u64 v)
 {

@@ -44,52 +44,63 @@ HC_DEV u32 rle_eq_mask16(const uint4 &v, u32 prev)
 }
 
 // Output of one 16-element vector.  e: equality bits 0..16 (bit 16 = the element after the vector),
-// valid: bits of existing elements, k0: run index of element 0 if it continues a run (else unused).
-//   lit bit k  : element k emits its byte          (run index q < 3)
-//   cnt bit k  : element k emits a count byte      (last of its run, 2 <= q < 257)
-// Fast path (no element can reach run index 257): pure bit logic, see SURVEY.md A.3.
-// Returns false if the vector needs the scalar path (a run of >= 257 elements passes through it).
-HC_DEV bool rle_vec_masks(u32 e, u32 valid, u32 &k0, u32 &lit, u32 &cnt)
+// valid: bits of existing elements, k0: run index of element 0 if it continues a run (else unused;
+// on return reduced modulo 258).
+//   lit bit k  : element k emits its byte          (run index q = k mod 258 < 3)
+//   cnt bit k  : element k emits the byte q - 2    (last of its run with 2 <= q < 257, or q == 257:
+//                the marker 255 of src/transform.cpp:259-263 is 257 - 2)
+// Pure bit logic.  Runs that start inside the vector cannot reach q = 257; only the
+// leading segment (the elements that continue the incoming run) can, and is patched arithmetically.
+HC_DEV void rle_vec_masks(u32 e, u32 valid, u32 &k0, u32 &lit, u32 &cnt)
 {
     const bool cont = e & 1u;
-    if (cont && k0 + 16u >= 257u) {
-        // inside a long run: the index wraps at 258 (src/transform.cpp:259-263).  Reduce it; the bit
-        // logic below stays exact as long as the leading segment of this vector neither restarts
-        // (q < 3 again) nor reaches q == 257.
-        const u32 r0 = k0 % 258u;
-        const u32 p = (u32)ffs((~e & 0xffffu) | 0x10000u) - 1u;   // elements (0..16) that continue the incoming run
-        if (r0 < 3u || r0 + p > 257u) return false;
-        k0 = r0;
-    }
-    const u32 b1 = (cont && k0 >= 2u) ? 2u : 0u, b2 = (cont && k0 >= 3u) ? 1u : 0u;
-    const u32 x = ((e & 0xffffu) << 2) | b1 | b2;     // bit k+2 = e_k, bits 1,0 = e_-1, e_-2
+    const bool deep = cont && k0 + 16u >= 257u;
+    if (deep) k0 %= 258u;
+    // bits 1,0 = "e_-1", "e_-2": whether the incoming run already holds >= 2 / >= 3 elements; inside
+    // a long run pretend it does and fix the leading segment below
+    const u32 b1 = (cont && (deep || k0 >= 2u)) ? 2u : 0u, b2 = (cont && (deep || k0 >= 3u)) ? 1u : 0u;
+    const u32 x = ((e & 0xffffu) << 2) | b1 | b2;     // bit k+2 = e_k
     const u32 q2 = (x >> 2) & (x >> 1);               // e_k & e_k-1           (q >= 2)
     const u32 q3 = q2 & x;                            // ... & e_k-2           (q >= 3)
     lit = valid & ~q3;
     cnt = valid & q2 & ~(e >> 1);                     // run ends here (next element does not continue)
-    return true;
+    if (deep) {
+        const u32 p = (u32)ffs((~e & 0xffffu) | 0x10000u) - 1u;   // elements 0..p-1 continue the incoming run (p >= 1)
+        const u32 lead = (1u << p) - 1u;
+        const u32 kw = 257u - k0;                                 // element with q == 257 (may lie beyond the vector)
+        u32 litl = k0 < 3u ? (1u << (3u - k0)) - 1u : 0u;         // q < 3 at the start ...
+        u32 m255 = 0u;
+        if (kw < 16u) { litl |= 7u << (kw + 1u); m255 = 1u << kw; }   // ... and after the wrap
+        u32 qe = k0 + p - 1u;                                     // run index of the segment's last element
+        if (qe >= 258u) qe -= 258u;
+        const u32 endbit = cnt & (1u << (p - 1u));                // set iff the run ends there
+        lit = (lit & ~lead) | (litl & lead & valid);
+        cnt = (cnt & ~lead) | ((qe >= 2u && qe < 257u) ? endbit : 0u) | (m255 & lead & valid);
+    }
 }
 
-// run index of element k inside a vector (fast path only: no wrap inside the vector)
+// run index modulo 258 of element k of a vector (k0: as returned by rle_vec_masks)
 HC_DEV u32 rle_run_index(u32 e, u32 k0, u32 k)
 {
     const u32 zeros = ~e & ((2u << k) - 1u);          // run starts at or below k
-    return zeros ? k - (31u - (u32)clz(zeros)) : k0 + k;
+    if (zeros) return k - (31u - (u32)clz(zeros));
+    const u32 q = k0 + k;
+    return q >= 258u ? q - 258u : q;
 }
 
-// byte-granular writer into the shared staging buffer: words are assembled in a 64-bit register,
+// byte-granular writer into the shared staging buffer: bytes are assembled in a register pair,
 // full words go out as STS.32, the ragged first/last bytes as STS.U8 (neighbouring threads own the
 // other bytes of those words)
 struct StageWriter {
-    u64 buf;
-    u32 fill;      // bytes in buf (including the leading filler of the first word)
+    u32 lo, hi;    // lo: the word being assembled (fill < 4 valid bytes between calls)
+    u32 fill;      // bytes in lo (including the leading filler of the first word)
     u32 waddr;     // shared address of the word being assembled
     u32 skip;      // filler bytes of the first word still to be skipped (0 after the first flush)
 };
 
 HC_DEV void sw_init(StageWriter &w, u32 stage_addr, u32 o)
 {
-    w.buf = 0;
+    w.lo = 0; w.hi = 0;
     w.fill = o & 3u;
     w.skip = o & 3u;
     w.waddr = stage_addr + (o & ~3u);
@@ -97,39 +108,68 @@ HC_DEV void sw_init(StageWriter &w, u32 stage_addr, u32 o)
 
 HC_DEV void sw_flush_word(StageWriter &w)
 {
-    const u32 word = (u32)w.buf;
     if (w.skip) {
-        for (u32 i = w.skip; i < 4u; i++) sts8(w.waddr + i, word >> (8u * i));
+        for (u32 i = w.skip; i < 4u; i++) sts8(w.waddr + i, w.lo >> (8u * i));
         w.skip = 0;
     } else {
-        sts32(w.waddr, word);
+        sts32(w.waddr, w.lo);
     }
     w.waddr += 4u;
-    w.buf >>= 32;
+    w.lo = w.hi;
+    w.hi = 0;
     w.fill -= 4u;
 }
 
-HC_DEV void sw_put_byte(StageWriter &w, u32 b)
+// append the low nb (0..4) bytes of x; the bytes of x above nb must be zero
+HC_DEV void sw_put(StageWriter &w, u32 x, u32 nb)
 {
-    w.buf |= (u64)(b & 0xffu) << (8u * w.fill);
-    if (++w.fill >= 4u) sw_flush_word(w);
+    const u32 s = 8u * w.fill;
+    w.lo |= x << s;
+    w.hi = funnel_l(x, 0u, s);          // bytes that spill into the next word (0 when s == 0)
+    w.fill += nb;
+    if (w.fill >= 4u) sw_flush_word(w);
 }
 
-HC_DEV void sw_put_word(StageWriter &w, u32 x)     // 4 bytes at once
-{
-    w.buf |= (u64)x << (8u * w.fill);
-    w.fill += 4u;
-    sw_flush_word(w);
-}
+HC_DEV void sw_put_byte(StageWriter &w, u32 b) { sw_put(w, b & 0xffu, 1u); }
+HC_DEV void sw_put_word(StageWriter &w, u32 x) { sw_put(w, x, 4u); }
 
 HC_DEV void sw_finish(StageWriter &w)
 {
-    const u32 word = (u32)w.buf;
-    for (u32 i = w.skip; i < w.fill; i++) sts8(w.waddr + i, word >> (8u * i));
+    for (u32 i = w.skip; i < w.fill; i++) sts8(w.waddr + i, w.lo >> (8u * i));
+}
+
+// Compaction table of the encoder.  Index = m4 | b4 << 4 for one 4-element word: m4 = elements that
+// emit their byte (a literal, or a count already substituted into the word), b4 (subset of m4) =
+// elements followed by a count byte 0 (a run of exactly three ends there).  Entry = two PRMT
+// selectors (low / high output word) that move the kept bytes together and insert the zero bytes
+// (selector nibble 4 = byte 0 of the second PRMT operand, which is zero).
+HC_DEV u32 *rle_enc_lut()
+{
+    HC_SHARED u32 lut[256];
+    return lut;
+}
+
+// called once per kernel by all TPB threads before the first rle_encode_stream
+HC_DEV void rle_enc_init()
+{
+    u32 *lut = rle_enc_lut();
+    const u32 idx = threadIdx.x & 255u, m4 = idx & 15u, b4 = idx >> 4;
+    u64 sel = 0x4444444444444444ull;
+    u32 o = 0;
+    for (u32 k = 0; k < 4u; k++) {
+        if ((m4 >> k) & 1u) {
+            sel = (sel & ~(0xfull << (4u * o))) | ((u64)k << (4u * o));
+            o++;
+            if ((b4 >> k) & 1u) o++;                  // nibble stays 4: a zero byte
+        }
+    }
+    lut[idx] = (u32)(sel & 0xffffu) | ((u32)((sel >> 16) & 0xffffu) << 16);
+    syncthreads();
 }
 
 // Encodes the n-byte stream at src (16-byte aligned) to dst (any alignment); called by all TPB
-// threads of a CTA, returns the number of bytes written.  Ends with a CTA barrier.
+// threads of a CTA, returns the number of bytes written.  Ends with a CTA barrier.  The kernel must
+// have called rle_enc_init() before.
 HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT dst)
 {
     HC_SHARED u32 wtot[2][32];
@@ -139,6 +179,7 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 stage = smem_addr(sout);
     const u32 dphase = (u32)((uintptr_t)dst & 15u);
+    const u32 *lut = rle_enc_lut();
     {
         {
         u64 out_pos = 0;      // bytes emitted by all previous tiles
@@ -183,34 +224,21 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
 
             // ---- per-vector output masks and counts ----------------------------------------
             u32 cnt[UN], oexcl[UN], k0v[UN], lit[UN], cbm[UN];
-            u32 slowm = 0;   // bit j: vector j takes the scalar path (a run >= 257 passes through it)
 #pragma unroll
             for (int j = 0; j < UN; j++) {
                 const u32 tp = (u32)j * SUB_BYTES + tid * 16;   // tile-relative position
-                const u32 k0 = sexcl[j] ? tp - (sexcl[j] - 1u) : carry_run + tp;   // true run index of element 0
-                u32 kr = k0;                                                      // reduced mod 258 if needed
-                u32 c;
-                if (rle_vec_masks(eq[j], valid[j], kr, lit[j], cbm[j])) {
-                    k0v[j] = kr;
-                    c = (u32)popc(lit[j]) + (u32)popc(cbm[j]);
-                } else {
-                    k0v[j] = k0;
-                    slowm |= 1u << j;
-                    u32 q = k0 % 258u;
-                    c = 0;
-                    for (int k = 0; k < 16; k++) {
-                        if (k > 0) q = ((eq[j] >> k) & 1u) ? (q == 257u ? 0u : q + 1u) : 0u;
-                        const bool is_end = !((eq[j] >> (k + 1)) & 1u);
-                        const u32 ck = (q < 3u ? 1u : 0u) + (q == 257u ? 1u : 0u) + ((is_end && q >= 2u && q != 257u) ? 1u : 0u);
-                        c += ((valid[j] >> k) & 1u) ? ck : 0u;
-                    }
-                }
-                cnt[j] = c;
+                u32 k0 = sexcl[j] ? tp - (sexcl[j] - 1u) : carry_run + tp;   // run index of element 0
                 if (j == UN - 1 && tid == TPB - 1) {
-                    // length of the run that ends at the last element of a full tile
+                    // length of the run that ends at the last element of a full tile (kept below
+                    // 2^15 + 258: only its value modulo 258 and "is it long" matter)
                     const u32 st = valid[j] & ~eq[j];
-                    s_carry_run = st ? 16u - (31u - (u32)clz(st)) : ((eq[j] & 1u) ? k0 + 16u : 16u);
+                    u32 cr = st ? 16u - (31u - (u32)clz(st)) : ((eq[j] & 1u) ? k0 + 16u : 16u);
+                    if (cr >= 258u * 128u) cr = 258u * 64u + cr % 258u;
+                    s_carry_run = cr;
                 }
+                rle_vec_masks(eq[j], valid[j], k0, lit[j], cbm[j]);
+                k0v[j] = k0;
+                cnt[j] = (u32)popc(lit[j]) + (u32)popc(cbm[j]);
             }
             u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
 
@@ -221,29 +249,28 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
                 if (cnt[j] == 0) continue;
                 StageWriter w;
                 sw_init(w, stage, shift + oexcl[j]);
-                if (!((slowm >> j) & 1u)) {
-                    if (lit[j] == 0xffffu && cbm[j] == 0u) {          // all literals: the vector goes out verbatim
-                        sw_put_word(w, cur[j].x); sw_put_word(w, cur[j].y);
-                        sw_put_word(w, cur[j].z); sw_put_word(w, cur[j].w);
-                    } else {
-                        u32 m = lit[j] | cbm[j];
-                        while (m) {
-                            const u32 k = (u32)ffs(m) - 1u;
-                            m &= m - 1u;
-                            if ((lit[j] >> k) & 1u) sw_put_byte(w, vec_byte(cur[j], (int)k));
-                            if ((cbm[j] >> k) & 1u) sw_put_byte(w, rle_run_index(eq[j], k0v[j], k) - 2u);
-                        }
-                    }
+                if (lit[j] == 0xffffu && cbm[j] == 0u) {              // all literals: the vector goes out verbatim
+                    sw_put_word(w, cur[j].x); sw_put_word(w, cur[j].y);
+                    sw_put_word(w, cur[j].z); sw_put_word(w, cur[j].w);
                 } else {
-                    u32 q = k0v[j] % 258u;
-                    for (int k = 0; k < 16; k++) {
-                        if (k > 0) q = ((eq[j] >> k) & 1u) ? (q == 257u ? 0u : q + 1u) : 0u;
-                        if ((valid[j] >> k) & 1u) {
-                            const bool is_end = !((eq[j] >> (k + 1)) & 1u);
-                            if (q < 3u) sw_put_byte(w, vec_byte(cur[j], k));
-                            if (q == 257u) sw_put_byte(w, 255u);
-                            else if (is_end && q >= 2u) sw_put_byte(w, q - 2u);
+                    // word by word: substitute the count of a run that ends on a non-literal element
+                    // into its byte (at most one per word: such elements are >= 4 apart), then compact
+                    const u32 keep = lit[j] | cbm[j], both = lit[j] & cbm[j], sub = cbm[j] & ~lit[j];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        u32 x = i == 0 ? cur[j].x : i == 1 ? cur[j].y : i == 2 ? cur[j].z : cur[j].w;
+                        const u32 s4 = (sub >> (4 * i)) & 15u;
+                        if (s4) {
+                            const u32 kk = (u32)ffs(s4) - 1u;
+                            const u32 val = rle_run_index(eq[j], k0v[j], 4u * i + kk) - 2u;
+                            x = (x & ~(0xffu << (8u * kk))) | (val << (8u * kk));
                         }
+                        const u32 idx = ((keep >> (4 * i)) & 15u) | (((both >> (4 * i)) & 15u) << 4);
+                        const u32 nb = (u32)popc(idx);
+                        if (nb == 0u) continue;
+                        const u32 e = lut[idx];
+                        sw_put(w, prmt(x, 0u, e & 0xffffu), nb < 4u ? nb : 4u);
+                        if (nb > 4u) sw_put(w, prmt(x, 0u, e >> 16), nb - 4u);
                     }
                 }
                 sw_finish(w);
@@ -279,6 +306,7 @@ HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
 rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u64 *HC_RESTRICT out_len, u32 nf)
 {
+    rle_enc_init();
     for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
         const u64 m = rle_encode_stream(in + in_off[f], in_len[f], out + out_off[f]);
         if (threadIdx.x == 0) out_len[f] = m;

@@ -370,6 +370,13 @@ def test_rle_encode_long_runs(be, oracle):
             parts.append(np.full(L + int(rng.integers(0, 3)), v))
             parts.append(np.array([(v + 1) & 255] * int(rng.integers(1, 4))))
         files.append(np.concatenate(parts).astype(np.uint8))
+    # random mixtures of short runs and runs around the multiples of 258
+    pool = np.array([1, 1, 1, 2, 3, 3, 4, 5, 6, 7, 16, 17, 255, 256, 257, 258, 259, 260, 261, 262, 514, 515, 516, 517, 518,
+                     519, 520, 521, 773, 774, 775, 776])
+    for _ in range(24):
+        ls = rng.choice(pool, 40)
+        vals = rng.integers(0, 3, 40)                 # few values: neighbouring runs often merge
+        files.append(np.concatenate([np.full(int(L), int(v)) for L, v in zip(ls, vals)]).astype(np.uint8))
     files.append(np.full(40000, 5, np.uint8))
     files.append(np.concatenate([np.full(16384 * 2 - 1, 9), np.full(300, 9), np.full(2, 1)]).astype(np.uint8))
     src = Batch(be, [f.size for f in files], files)
