@@ -51,7 +51,7 @@ HC_DEV u32 rle_eq_mask16(const uint4 &v, u32 prev)
 //                the marker 255 of src/transform.cpp:259-263 is 257 - 2)
 // Pure bit logic.  Runs that start inside the vector cannot reach q = 257; only the
 // leading segment (the elements that continue the incoming run) can, and is patched arithmetically.
-HC_DEV void rle_vec_masks(u32 e, u32 valid, u32 &k0, u32 &lit, u32 &cnt)
+HC_DEV void rle_vec_masks_impl(u32 e, u32 valid, u32 &k0, u32 &lit, u32 &cnt)
 {
     const bool cont = e & 1u;
     const bool deep = cont && k0 + 16u >= 257u;
@@ -77,6 +77,16 @@ HC_DEV void rle_vec_masks(u32 e, u32 valid, u32 &k0, u32 &lit, u32 &cnt)
         lit = (lit & ~lead) | (litl & lead & valid);
         cnt = (cnt & ~lead) | ((qe >= 2u && qe < 257u) ? endbit : 0u) | (m255 & lead & valid);
     }
+}
+
+// out-of-line copy (the streaming kernels are instruction-cache bound when everything is inlined four
+// times): lit | cnt << 16 in .x, the reduced k0 in .y
+HC_DEV_NOINLINE uint2 rle_vec_masks(u32 e, u32 valid, u32 k0)
+{
+    u32 lit, cnt;
+    rle_vec_masks_impl(e, valid, k0, lit, cnt);
+    uint2 r; r.x = lit | (cnt << 16); r.y = k0;
+    return r;
 }
 
 // run index modulo 258 of element k of a vector (k0: as returned by rle_vec_masks)
@@ -167,6 +177,38 @@ HC_DEV void rle_enc_init()
     syncthreads();
 }
 
+// writes the output bytes of one vector (masks from rle_vec_masks) to the staging buffer at byte o
+HC_DEV_NOINLINE void rle_stage_vector(uint4 v, u32 lit, u32 cbm, u32 eq, u32 k0, u32 stage, u32 o, const u32 *lut)
+{
+    StageWriter w;
+    sw_init(w, stage, o);
+    if (lit == 0xffffu && cbm == 0u) {                    // all literals: the vector goes out verbatim
+        sw_put_word(w, v.x); sw_put_word(w, v.y);
+        sw_put_word(w, v.z); sw_put_word(w, v.w);
+    } else {
+        // word by word: substitute the count of a run that ends on a non-literal element into its
+        // byte (at most one per word: such elements are >= 4 apart), then compact
+        const u32 keep = lit | cbm, both = lit & cbm, sub = cbm & ~lit;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            u32 x = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+            const u32 s4 = (sub >> (4 * i)) & 15u;
+            if (s4) {
+                const u32 kk = (u32)ffs(s4) - 1u;
+                const u32 val = rle_run_index(eq, k0, 4u * i + kk) - 2u;
+                x = (x & ~(0xffu << (8u * kk))) | (val << (8u * kk));
+            }
+            const u32 idx = ((keep >> (4 * i)) & 15u) | (((both >> (4 * i)) & 15u) << 4);
+            const u32 nb = (u32)popc(idx);
+            if (nb == 0u) continue;
+            const u32 e = lut[idx];
+            sw_put(w, prmt(x, 0u, e & 0xffffu), nb < 4u ? nb : 4u);
+            if (nb > 4u) sw_put(w, prmt(x, 0u, e >> 16), nb - 4u);
+        }
+    }
+    sw_finish(w);
+}
+
 // Encodes the n-byte stream at src (16-byte aligned) to dst (any alignment); called by all TPB
 // threads of a CTA, returns the number of bytes written.  Ends with a CTA barrier.  The kernel must
 // have called rle_enc_init() before.
@@ -185,17 +227,26 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
         u64 out_pos = 0;      // bytes emitted by all previous tiles
         u32 carry_run = 0;    // length of the run that ends at the last element of the previous tile
 
+        // halo: lane 0 needs the byte before its vector, lane 31 the byte after (other lanes get them
+        // by shuffle); fetched one tile ahead like the vectors themselves
         uint4 cur[UN], nxt[UN];
+        u32 hcur[UN], hnxt[UN];
 #pragma unroll
         for (int j = 0; j < UN; j++) {
             u64 p = (u64)j * SUB_BYTES + tid * 16;
             cur[j] = p < n ? ldg16(src + p) : make_uint4_zero();
+            hcur[j] = 0x100u;
+            if (lane == 0 && p > 0 && p < n) hcur[j] = ldg8(src + p - 1);
+            if (lane == 31 && p + 16 < n) hcur[j] = ldg8(src + p + 16);
         }
         for (u64 t0 = 0; t0 < n; t0 += TILE_BYTES) {
 #pragma unroll
             for (int j = 0; j < UN; j++) {
                 u64 p = t0 + TILE_BYTES + (u64)j * SUB_BYTES + tid * 16;
                 nxt[j] = p < n ? ldg16(src + p) : make_uint4_zero();
+                hnxt[j] = 0x100u;
+                if (lane == 0 && p < n) hnxt[j] = ldg8(src + p - 1);
+                if (lane == 31 && p + 16 < n) hnxt[j] = ldg8(src + p + 16);
             }
             // ---- equality bits and run starts ------------------------------------------
             u32 eq[UN];      // bit k (0..16): element k equals element k-1 (bit 16 = next thread's first)
@@ -206,8 +257,8 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
                 const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
                 const u32 first = cur[j].x & 0xffu, last = cur[j].w >> 24;
                 u32 pb = shfl_up(last, 1), nb = shfl_down(first, 1);
-                if (lane == 0) pb = (p > 0 && p < n) ? ldg8(src + p - 1) : 0x100u;
-                if (lane == 31) nb = (p + 16 < n) ? ldg8(src + p + 16) : 0x100u;
+                if (lane == 0) pb = hcur[j];
+                if (lane == 31) nb = hcur[j];
                 u32 e = rle_eq_mask16(cur[j], pb);
                 if (nb == last) e |= 1u << 16;
                 const u32 vm = p >= n ? 0u : (n - p >= 17 ? 0x1ffffu : ((1u << (u32)(n - p)) - 1u));
@@ -236,9 +287,11 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
                     if (cr >= 258u * 128u) cr = 258u * 64u + cr % 258u;
                     s_carry_run = cr;
                 }
-                rle_vec_masks(eq[j], valid[j], k0, lit[j], cbm[j]);
-                k0v[j] = k0;
-                cnt[j] = (u32)popc(lit[j]) + (u32)popc(cbm[j]);
+                const uint2 mk = rle_vec_masks(eq[j], valid[j], k0);
+                lit[j] = mk.x & 0xffffu;
+                cbm[j] = mk.x >> 16;
+                k0v[j] = mk.y;
+                cnt[j] = (u32)popc(mk.x);
             }
             u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
 
@@ -247,33 +300,7 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
 #pragma unroll
             for (int j = 0; j < UN; j++) {
                 if (cnt[j] == 0) continue;
-                StageWriter w;
-                sw_init(w, stage, shift + oexcl[j]);
-                if (lit[j] == 0xffffu && cbm[j] == 0u) {              // all literals: the vector goes out verbatim
-                    sw_put_word(w, cur[j].x); sw_put_word(w, cur[j].y);
-                    sw_put_word(w, cur[j].z); sw_put_word(w, cur[j].w);
-                } else {
-                    // word by word: substitute the count of a run that ends on a non-literal element
-                    // into its byte (at most one per word: such elements are >= 4 apart), then compact
-                    const u32 keep = lit[j] | cbm[j], both = lit[j] & cbm[j], sub = cbm[j] & ~lit[j];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        u32 x = i == 0 ? cur[j].x : i == 1 ? cur[j].y : i == 2 ? cur[j].z : cur[j].w;
-                        const u32 s4 = (sub >> (4 * i)) & 15u;
-                        if (s4) {
-                            const u32 kk = (u32)ffs(s4) - 1u;
-                            const u32 val = rle_run_index(eq[j], k0v[j], 4u * i + kk) - 2u;
-                            x = (x & ~(0xffu << (8u * kk))) | (val << (8u * kk));
-                        }
-                        const u32 idx = ((keep >> (4 * i)) & 15u) | (((both >> (4 * i)) & 15u) << 4);
-                        const u32 nb = (u32)popc(idx);
-                        if (nb == 0u) continue;
-                        const u32 e = lut[idx];
-                        sw_put(w, prmt(x, 0u, e & 0xffffu), nb < 4u ? nb : 4u);
-                        if (nb > 4u) sw_put(w, prmt(x, 0u, e >> 16), nb - 4u);
-                    }
-                }
-                sw_finish(w);
+                rle_stage_vector(cur[j], lit[j], cbm[j], eq[j], k0v[j], stage, shift + oexcl[j], lut);
             }
             syncthreads();
             carry_run = s_carry_run;
@@ -294,7 +321,7 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
             }
             out_pos += total;
 #pragma unroll
-            for (int j = 0; j < UN; j++) cur[j] = nxt[j];
+            for (int j = 0; j < UN; j++) { cur[j] = nxt[j]; hcur[j] = hnxt[j]; }
             syncthreads();
         }
         return out_pos;
