@@ -146,6 +146,7 @@ adapt_expand_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_of
                           const u32 *HC_RESTRICT blk_start, u64 blk_stride, const i32 *HC_RESTRICT status, u32 nf,
                           u8 *HC_RESTRICT tmp, u64 tstride)
 {
+    rle_dec_init();
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
         if (status[f] != 0) continue;
         const u8 *src = in + in_off[f];

@@ -98,6 +98,11 @@ HC_DEV int clzll(u64 v) { return v ? __builtin_clzll(v) : 64; }
 HC_DEV int ffs(u32 v) { return __builtin_ffs((int)v); }
 HC_DEV int ffsll(u64 v) { return __builtin_ffsll((long long)v); }
 HC_DEV u32 bswap32(u32 v) { return __builtin_bswap32(v); }
+HC_DEV u32 dp4a_u(u32 a, u32 b, u32 c)
+{
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+    return c;
+}
 // PRMT in its default mode: result byte i = byte (sel nibble i) of the 8 bytes {b:a}
 HC_DEV u32 prmt(u32 a, u32 b, u32 sel)
 {
@@ -175,6 +180,7 @@ HC_DEV int ffs(u32 v) { return __ffs((int)v); }
 HC_DEV int ffsll(u64 v) { return __ffsll((long long)v); }
 HC_DEV u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
 HC_DEV u32 prmt(u32 a, u32 b, u32 sel) { return __byte_perm(a, b, sel); }
+HC_DEV u32 dp4a_u(u32 a, u32 b, u32 c) { return __dp4a(a, b, c); }
 HC_DEV u32 brev(u32 v) { return __brev(v); }
 HC_DEV u64 bswap64(u64 v)
 {

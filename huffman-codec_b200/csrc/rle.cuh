@@ -359,171 +359,271 @@ struct OpCompose { HC_DEVM u32 operator()(u32 a, u32 b) const { return map_compo
 
 constexpr u32 DEC_WIN = TPB * 64;   // 16 KiB of output per expansion window
 
+// Tables of the decoder, indexed by 8 consecutive equality bits (bit k: byte k equals byte k-1):
+//   map8[e8]        the state map of those 8 bytes
+//   cls8[s][e8]     entering in state s: bits 0..7 = which of the 8 bytes are COUNT bytes (read in
+//                   state 3), bits 8..9 = the state after them
+struct RleDecTables {
+    u8 map8[256];
+    u16 cls8[4][256];
+};
+
+HC_DEV RleDecTables *rle_dec_tables()
+{
+    HC_SHARED RleDecTables t;
+    return &t;
+}
+
+// called once per kernel by all TPB threads before the first rle_decode_stream
+HC_DEV void rle_dec_init()
+{
+    RleDecTables *t = rle_dec_tables();
+    const u32 e8 = threadIdx.x & 255u;
+    u32 m = MAP_ID;
+    for (u32 k = 0; k < 8u; k++) m = map_compose(m, ((e8 >> k) & 1u) ? MAP_EQ : MAP_NE);
+    t->map8[e8] = (u8)m;
+    for (u32 s0 = 0; s0 < 4u; s0++) {
+        u32 st = s0, cm = 0;
+        for (u32 k = 0; k < 8u; k++) {
+            if (st == 3u) { cm |= 1u << k; st = 0; }
+            else st = (st == 0u) ? 1u : (((e8 >> k) & 1u) ? st + 1u : 1u);
+        }
+        t->cls8[s0][e8] = (u16)(cm | (st << 8));
+    }
+    syncthreads();
+}
+
+// state map of the valid bytes of a ragged vector (first / last vector of a stream)
+HC_DEV_NOINLINE u32 rle_dec_map_partial(u32 e, u32 vm)
+{
+    u32 m = MAP_ID;
+    for (u32 k = 0; k < 16u; k++)
+        if ((vm >> k) & 1u) m = map_compose(m, ((e >> k) & 1u) ? MAP_EQ : MAP_NE);
+    return m;
+}
+
+// count-byte mask of the valid bytes of a ragged vector entered in state st
+HC_DEV_NOINLINE u32 rle_dec_cls_partial(u32 e, u32 vm, u32 st)
+{
+    u32 cm = 0;
+    for (u32 k = 0; k < 16u; k++) {
+        if (!((vm >> k) & 1u)) continue;
+        if (st == 3u) { cm |= 1u << k; st = 0; }
+        else st = (st == 0u) ? 1u : (((e >> k) & 1u) ? st + 1u : 1u);
+    }
+    return cm;
+}
+
+// spread the low 4 bits of m to the four byte lanes of a word (0xff per set bit)
+HC_DEV u32 spread4(u32 m) { return (((m & 15u) * 0x00204081u) & 0x01010101u) * 0xffu; }
+
+// sum of the bytes of v selected by the 16-bit mask cm
+HC_DEV u32 rle_masked_byte_sum(const uint4 &v, u32 cm)
+{
+    return dp4a_u(v.x & spread4(cm), 0x01010101u, 0u) + dp4a_u(v.y & spread4(cm >> 4), 0x01010101u, 0u) +
+           dp4a_u(v.z & spread4(cm >> 8), 0x01010101u, 0u) + dp4a_u(v.w & spread4(cm >> 12), 0x01010101u, 0u);
+}
+
+// generic expansion of one vector into the current output window [w0, w1): every token drops its
+// value and a head flag at its first output position inside the window
+HC_DEV_NOINLINE void rle_dec_scatter(uint4 v, u32 vm, u32 cm, u32 pb, u32 o, u32 w0, u32 w1, u8 *sval, u32 *heads)
+{
+    u32 prev = pb;
+#pragma unroll 4
+    for (int k = 0; k < 16; k++) {
+        const u32 b = vec_byte(v, k);
+        if ((vm >> k) & 1u) {
+            const bool is_cnt = (cm >> k) & 1u;
+            const u32 len = is_cnt ? b : 1u, val = is_cnt ? prev : b;
+            if (len && o < w1 && o + len > w0) {
+                const u32 pos = (o > w0 ? o : w0) - w0;
+                sval[pos] = (u8)val;
+                atomic_or_shared(&heads[pos >> 5], 1u << (pos & 31u));
+            }
+            o += len;
+        }
+        prev = b;
+    }
+}
+
+// the common case of rle_dec_scatter: 16 literals that all lie inside the window, at window offset pos
+HC_DEV_NOINLINE void rle_dec_scatter_literals(uint4 v, u32 pos, u32 sval_addr, u32 *heads)
+{
+    StageWriter w;
+    sw_init(w, sval_addr, pos);
+    sw_put_word(w, v.x); sw_put_word(w, v.y); sw_put_word(w, v.z); sw_put_word(w, v.w);
+    sw_finish(w);
+    const u32 sh = pos & 31u;
+    atomic_or_shared(&heads[pos >> 5], 0xffffu << sh);
+    if (sh > 16u) atomic_or_shared(&heads[(pos >> 5) + 1u], 0xffffu >> (32u - sh));
+}
+
+// fills 16 output bytes from the head flags hb / values at sval + wbase, carrying the current value
+struct Fill16 { uint4 r; u32 c; };
+HC_DEV_NOINLINE Fill16 rle_dec_fill16(u32 hb, const u8 *sv, u32 c)
+{
+    u32 wv[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if ((hb >> k) & 1u) c = sv[k];
+        wv[k >> 2] |= c << (8 * (k & 3));
+    }
+    Fill16 f;
+    f.r.x = wv[0]; f.r.y = wv[1]; f.r.z = wv[2]; f.r.w = wv[3];
+    f.c = c;
+    return f;
+}
+
 // Decodes the n0-byte token stream at src0 (any alignment) to dst (16-byte aligned, or null to
 // only measure), writing at most cap bytes; called by all TPB threads of a CTA, returns the decoded
 // length.  An unaligned stream is read from the 16-byte boundary below it with the leading bytes
 // masked out (they belong to the caller's buffer: a header or the previous block's tokens).
+// The kernel must have called rle_dec_init() before.
 HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT dst, u64 cap)
 {
     HC_SHARED u32 wtot[2][32];
     HC_SHARED u32 wlast[NW];
-    HC_SHARED u32 heads[DEC_WIN / 32];
+    HC_SHARED u32 heads[DEC_WIN / 32 + 1];
     HC_SHARED HC_ALIGNED16 u8 sval[DEC_WIN];
+    HC_SMEM_ARENA(wtot);
+    const RleDecTables *tb = rle_dec_tables();
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u32 lead = n0 ? (u32)((uintptr_t)src0 & 15u) : 0u;
     const u8 *src = src0 - lead;
     const u64 n = n0 + lead;
-    {
-        {
-        u64 out_pos = 0;
-        u32 carry_state = 0;
+    const u32 sval_addr = smem_addr(sval);
+    u64 out_pos = 0;
+    u32 carry_state = 0;
 
-        uint4 cur[UN], nxt[UN];
+    uint4 cur[UN], nxt[UN];
+    u32 hcur[UN], hnxt[UN];          // lane 0: the byte before its vector (prefetched with the vector)
+#pragma unroll
+    for (int j = 0; j < UN; j++) {
+        u64 p = (u64)j * SUB_BYTES + tid * 16;
+        cur[j] = p < n ? ldg16(src + p) : make_uint4_zero();
+        hcur[j] = (lane == 0 && p > 0 && p < n) ? ldg8(src + p - 1) : 0u;
+    }
+    for (u64 t0 = 0; t0 < n; t0 += TILE_BYTES) {
 #pragma unroll
         for (int j = 0; j < UN; j++) {
-            u64 p = (u64)j * SUB_BYTES + tid * 16;
-            cur[j] = p < n ? ldg16(src + p) : make_uint4_zero();
+            u64 p = t0 + TILE_BYTES + (u64)j * SUB_BYTES + tid * 16;
+            nxt[j] = p < n ? ldg16(src + p) : make_uint4_zero();
+            hnxt[j] = (lane == 0 && p < n) ? ldg8(src + p - 1) : 0u;
         }
-        for (u64 t0 = 0; t0 < n; t0 += TILE_BYTES) {
+        // ---- scan 1: decoder state maps -----------------------------------------------
+        u32 eq[UN], valid[UN], pbyte[UN], fmap[UN], mexcl[UN];
 #pragma unroll
-            for (int j = 0; j < UN; j++) {
-                u64 p = t0 + TILE_BYTES + (u64)j * SUB_BYTES + tid * 16;
-                nxt[j] = p < n ? ldg16(src + p) : make_uint4_zero();
-            }
-            // ---- scan 1: decoder state maps -----------------------------------------------
-            u32 eq[UN], valid[UN], pbyte[UN], fmap[UN], mexcl[UN];
-#pragma unroll
-            for (int j = 0; j < UN; j++) {
-                const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
-                u32 last = cur[j].w >> 24;
-                u32 pb = shfl_up(last, 1);
-                if (lane == 0) pb = (p > 0 && p < n) ? ldg8(src + p - 1) : 0u;
-                pbyte[j] = pb;
-                u32 vm = p >= n ? 0u : (n - p >= 16 ? 0xffffu : ((1u << (u32)(n - p)) - 1u));
-                if (p == 0) vm &= ~((1u << lead) - 1u);
-                u32 e = 0, prev = pb, m = MAP_ID;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    u32 b = vec_byte(cur[j], k);
-                    bool same = (b == prev);
-                    if (same) e |= 1u << k;
-                    prev = b;
-                    if ((vm >> k) & 1u) m = map_compose(m, same ? MAP_EQ : MAP_NE);
-                }
-                eq[j] = e;
-                valid[j] = vm;
-                fmap[j] = m;
-            }
-            u32 tile_map = block_scan_striped(fmap, mexcl, MAP_ID, OpCompose(), wtot[0]);
+        for (int j = 0; j < UN; j++) {
+            const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
+            u32 pb = shfl_up(cur[j].w >> 24, 1);
+            if (lane == 0) pb = hcur[j];
+            pbyte[j] = pb;
+            u32 vm = p >= n ? 0u : (n - p >= 16 ? 0xffffu : ((1u << (u32)(n - p)) - 1u));
+            if (p == 0) vm &= ~((1u << lead) - 1u);
+            const u32 e = rle_eq_mask16(cur[j], pb);
+            eq[j] = e;
+            valid[j] = vm;
+            fmap[j] = vm == 0xffffu ? map_compose(tb->map8[e & 0xffu], tb->map8[(e >> 8) & 0xffu])
+                                    : (vm ? rle_dec_map_partial(e, vm) : MAP_ID);
+        }
+        u32 tile_map = block_scan_striped(fmap, mexcl, MAP_ID, OpCompose(), wtot[0]);
 
-            // ---- scan 2: output length of every token -------------------------------------
-            u32 st_in[UN], cnt[UN], oexcl[UN];
+        // ---- scan 2: which bytes are counts, output length of every vector ------------
+        u32 cmask[UN], cnt[UN], oexcl[UN];
 #pragma unroll
-            for (int j = 0; j < UN; j++) {
-                u32 s = map_apply(mexcl[j], carry_state);
-                st_in[j] = s;
-                u32 c = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    if ((valid[j] >> k) & 1u) {
-                        if (s == 3u) { c += vec_byte(cur[j], k); s = 0; }
-                        else { c += 1u; s = (s == 0u) ? 1u : (((eq[j] >> k) & 1u) ? s + 1u : 1u); }
-                    }
-                }
-                cnt[j] = c;
+        for (int j = 0; j < UN; j++) {
+            const u32 s = map_apply(mexcl[j], carry_state);
+            u32 cm;
+            if (valid[j] == 0xffffu) {
+                const u32 c0 = tb->cls8[s][eq[j] & 0xffu];
+                const u32 c1 = tb->cls8[c0 >> 8][(eq[j] >> 8) & 0xffu];
+                cm = (c0 & 0xffu) | ((c1 & 0xffu) << 8);
+            } else {
+                cm = valid[j] ? rle_dec_cls_partial(eq[j], valid[j], s) : 0u;
             }
-            u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
-            carry_state = map_apply(tile_map, carry_state);
+            cmask[j] = cm;
+            cnt[j] = (u32)popc(valid[j] & ~cm) + rle_masked_byte_sum(cur[j], cm);
+        }
+        u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
+        carry_state = map_apply(tile_map, carry_state);
 
-            // ---- expansion, one 16 KiB output window at a time ---------------------------
-            if (dst) {
-                const u32 shift = (u32)(out_pos & 15u);
-                // window coordinates: w = shift + tile-relative output position
-                for (u32 w0 = 0; w0 < shift + total; w0 += DEC_WIN) {
-                    const u32 w1 = w0 + DEC_WIN;
-                    for (u32 i = tid; i < DEC_WIN / 32; i += TPB) heads[i] = 0;
-                    syncthreads();
+        // ---- expansion, one 16 KiB output window at a time ---------------------------
+        if (dst) {
+            const u32 shift = (u32)(out_pos & 15u);
+            // window coordinates: w = shift + tile-relative output position
+            for (u32 w0 = 0; w0 < shift + total; w0 += DEC_WIN) {
+                const u32 w1 = w0 + DEC_WIN;
+                for (u32 i = tid; i < DEC_WIN / 32; i += TPB) heads[i] = 0;
+                syncthreads();
 #pragma unroll
-                    for (int j = 0; j < UN; j++) {
-                        u32 o = shift + oexcl[j];
-                        if (o < w1 && o + cnt[j] > w0) {
-                            u32 s = st_in[j], prev = pbyte[j];
-#pragma unroll
-                            for (int k = 0; k < 16; k++) {
-                                if ((valid[j] >> k) & 1u) {
-                                    u32 b = vec_byte(cur[j], k), len, val;
-                                    if (s == 3u) { len = b; val = prev; s = 0; }
-                                    else { len = 1; val = b; s = (s == 0u) ? 1u : (((eq[j] >> k) & 1u) ? s + 1u : 1u); }
-                                    if (len && o < w1 && o + len > w0) {
-                                        u32 pos = (o > w0 ? o : w0) - w0;
-                                        sval[pos] = (u8)val;
-                                        atomic_or_shared(&heads[pos >> 5], 1u << (pos & 31u));
-                                    }
-                                    o += len;
-                                    prev = b;
-                                }
-                            }
-                        }
-                    }
-                    syncthreads();
-                    // each thread fills 64 consecutive output bytes of the window
-                    u32 h0 = heads[2 * tid], h1 = heads[2 * tid + 1];
-                    u32 mylast = h1 ? 64u * tid + 32u + (31u - (u32)clz(h1)) + 1u
-                                    : (h0 ? 64u * tid + (31u - (u32)clz(h0)) + 1u : 0u);
-                    // exclusive max-scan over threads: last head before this thread's range
-                    u32 inc = mylast;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        u32 t = shfl_up(inc, d);
-                        if (lane >= (u32)d && t > inc) inc = t;
-                    }
-                    if (lane == 31) wlast[wid] = inc;
-                    syncthreads();
-                    u32 before = 0;
-                    for (u32 i = 0; i < wid; i++) before = wlast[i] > before ? wlast[i] : before;
-                    u32 le = shfl_up(inc, 1);
-                    if (lane == 0) le = 0;
-                    if (le > before) before = le;
-                    u32 curv = before ? sval[before - 1u] : 0u;
-                    const u32 lim = (shift + total - w0) < DEC_WIN ? (shift + total - w0) : DEC_WIN;  // valid bytes in window
-                    const u32 lo_valid = w0 == 0 ? shift : 0u;
-                    u8 *gbase = dst + (out_pos - shift) + w0;        // 16-byte aligned
-                    const u64 gpos0 = out_pos - shift + w0;          // file-relative position of window byte 0
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        u32 wbase = 64u * tid + 16u * c;
-                        u32 hb = ((c < 2 ? h0 : h1) >> (16u * (c & 1))) & 0xffffu;
-                        u32 wv[4] = {0, 0, 0, 0};
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            if ((hb >> k) & 1u) curv = sval[wbase + k];
-                            wv[k >> 2] |= curv << (8 * (k & 3));
-                        }
-                        if (wbase < lim) {
-                            u32 a = wbase < lo_valid ? lo_valid : wbase;
-                            u32 b = wbase + 16u > lim ? lim : wbase + 16u;
-                            // clip against the caller's capacity
-                            u64 capw = cap > gpos0 ? cap - gpos0 : 0;
-                            if (b > capw) b = (u32)capw;
-                            if (a == wbase && b == wbase + 16u) {
-                                uint4 r; r.x = wv[0]; r.y = wv[1]; r.z = wv[2]; r.w = wv[3];
-                                stg16(gbase + wbase, r);
-                            } else {
-                                for (u32 i = a; i < b; i++) gbase[i] = (u8)(wv[(i - wbase) >> 2] >> (8 * ((i - wbase) & 3)));
-                            }
-                        }
-                    }
-                    syncthreads();
+                for (int j = 0; j < UN; j++) {
+                    const u32 o = shift + oexcl[j];
+                    if (cnt[j] == 0u || o >= w1 || o + cnt[j] <= w0) continue;
+                    if (cmask[j] == 0u && valid[j] == 0xffffu && o >= w0 && o + 16u <= w1)
+                        rle_dec_scatter_literals(cur[j], o - w0, sval_addr, heads);
+                    else
+                        rle_dec_scatter(cur[j], valid[j], cmask[j], pbyte[j], o, w0, w1, sval, heads);
                 }
-            }
-            out_pos += total;
+                syncthreads();
+                // each thread fills 64 consecutive output bytes of the window
+                u32 h0 = heads[2 * tid], h1 = heads[2 * tid + 1];
+                u32 mylast = h1 ? 64u * tid + 32u + (31u - (u32)clz(h1)) + 1u
+                                : (h0 ? 64u * tid + (31u - (u32)clz(h0)) + 1u : 0u);
+                // exclusive max-scan over threads: last head before this thread's range
+                u32 inc = mylast;
 #pragma unroll
-            for (int j = 0; j < UN; j++) cur[j] = nxt[j];
-            syncthreads();
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 t = shfl_up(inc, d);
+                    if (lane >= (u32)d && t > inc) inc = t;
+                }
+                if (lane == 31) wlast[wid] = inc;
+                syncthreads();
+                u32 before = 0;
+                for (u32 i = 0; i < wid; i++) before = wlast[i] > before ? wlast[i] : before;
+                u32 le = shfl_up(inc, 1);
+                if (lane == 0) le = 0;
+                if (le > before) before = le;
+                u32 curv = before ? sval[before - 1u] : 0u;
+                const u32 lim = (shift + total - w0) < DEC_WIN ? (shift + total - w0) : DEC_WIN;  // valid bytes in window
+                const u32 lo_valid = w0 == 0 ? shift : 0u;
+                u8 *gbase = dst + (out_pos - shift) + w0;        // 16-byte aligned
+                const u64 gpos0 = out_pos - shift + w0;          // file-relative position of window byte 0
+                const u64 capw = cap > gpos0 ? cap - gpos0 : 0;  // clip against the caller's capacity
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const u32 wbase = 64u * tid + 16u * c;
+                    const u32 hb = ((c < 2 ? h0 : h1) >> (16u * (c & 1))) & 0xffffu;
+                    uint4 r;
+                    if (hb == 0xffffu) {                          // 16 literals: the values as they are
+                        r = *(const uint4 *)(sval + wbase);
+                        curv = r.w >> 24;
+                    } else if (hb == 0u) {                        // inside a run
+                        r.x = r.y = r.z = r.w = curv * 0x01010101u;
+                    } else {
+                        const Fill16 f = rle_dec_fill16(hb, sval + wbase, curv);
+                        r = f.r;
+                        curv = f.c;
+                    }
+                    if (wbase < lim) {
+                        u32 a = wbase < lo_valid ? lo_valid : wbase;
+                        u32 b = wbase + 16u > lim ? lim : wbase + 16u;
+                        if (b > capw) b = (u32)capw;
+                        if (a == wbase && b == wbase + 16u) {
+                            stg16(gbase + wbase, r);
+                        } else {
+                            for (u32 i = a; i < b; i++) gbase[i] = vec_byte(r, (int)(i - wbase));
+                        }
+                    }
+                }
+                syncthreads();
+            }
         }
-        return out_pos;
-        }
+        out_pos += total;
+#pragma unroll
+        for (int j = 0; j < UN; j++) { cur[j] = nxt[j]; hcur[j] = hnxt[j]; }
+        syncthreads();
     }
+    return out_pos;
 }
 
 HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
@@ -531,6 +631,7 @@ rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
                   u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
 {
+    rle_dec_init();
     for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
         const u64 cap = out ? out_cap[f] : 0;
         const u64 m = rle_decode_stream(in + in_off[f], in_len[f], out ? out + out_off[f] : (u8 *)0, cap);
