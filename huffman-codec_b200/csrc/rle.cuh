@@ -329,7 +329,7 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
     }
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
+HC_KERNEL HC_LAUNCH_BOUNDS(256, 3)
 rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u64 *HC_RESTRICT out_len, u32 nf)
 {
@@ -626,7 +626,7 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
     return out_pos;
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
+HC_KERNEL HC_LAUNCH_BOUNDS(256, 3)
 rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
                   u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
