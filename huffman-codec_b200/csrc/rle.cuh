@@ -118,8 +118,10 @@ HC_DEV void sw_init(StageWriter &w, u32 stage_addr, u32 o)
 
 HC_DEV void sw_flush_word(StageWriter &w)
 {
-    if (w.skip) {
-        for (u32 i = w.skip; i < 4u; i++) sts8(w.waddr + i, w.lo >> (8u * i));
+    if (w.skip) {                                      // bytes skip..3 (skip = 1..3), predicated stores
+        if (w.skip <= 1u) sts8(w.waddr + 1u, w.lo >> 8);
+        if (w.skip <= 2u) sts8(w.waddr + 2u, w.lo >> 16);
+        sts8(w.waddr + 3u, w.lo >> 24);
         w.skip = 0;
     } else {
         sts32(w.waddr, w.lo);
@@ -145,7 +147,32 @@ HC_DEV void sw_put_word(StageWriter &w, u32 x) { sw_put(w, x, 4u); }
 
 HC_DEV void sw_finish(StageWriter &w)
 {
-    for (u32 i = w.skip; i < w.fill; i++) sts8(w.waddr + i, w.lo >> (8u * i));
+    // bytes skip..fill-1 of the last word (fill <= 3)
+    if (w.skip == 0u && w.fill > 0u) sts8(w.waddr, w.lo);
+    if (w.skip <= 1u && w.fill > 1u) sts8(w.waddr + 1u, w.lo >> 8);
+    if (w.skip <= 2u && w.fill > 2u) sts8(w.waddr + 2u, w.lo >> 16);
+}
+
+// 16 bytes to the byte offset o of a shared staging buffer whose neighbouring bytes belong to other
+// threads: whole words where possible, byte stores for the two ragged words
+HC_DEV void stage_put16(u32 stage_addr, u32 o, const uint4 &v)
+{
+    const u32 r = o & 3u, a = stage_addr + (o & ~3u);
+    if (r == 0u) {
+        sts32(a, v.x); sts32(a + 4u, v.y); sts32(a + 8u, v.z); sts32(a + 12u, v.w);
+    } else {
+        const u32 s = 8u * r;
+        const u32 w0 = v.x << s, w4 = v.w >> (32u - s);
+        if (r <= 1u) sts8(a + 1u, w0 >> 8);
+        if (r <= 2u) sts8(a + 2u, w0 >> 16);
+        sts8(a + 3u, w0 >> 24);
+        sts32(a + 4u, funnel_l(v.x, v.y, s));
+        sts32(a + 8u, funnel_l(v.y, v.z, s));
+        sts32(a + 12u, funnel_l(v.z, v.w, s));
+        sts8(a + 16u, w4);
+        if (r >= 2u) sts8(a + 17u, w4 >> 8);
+        if (r >= 3u) sts8(a + 18u, w4 >> 16);
+    }
 }
 
 // Compaction table of the encoder.  Index = m4 | b4 << 4 for one 4-element word: m4 = elements that
@@ -180,12 +207,13 @@ HC_DEV void rle_enc_init()
 // writes the output bytes of one vector (masks from rle_vec_masks) to the staging buffer at byte o
 HC_DEV_NOINLINE void rle_stage_vector(uint4 v, u32 lit, u32 cbm, u32 eq, u32 k0, u32 stage, u32 o, const u32 *lut)
 {
+    if (lit == 0xffffu && cbm == 0u) {                    // all literals: the vector goes out verbatim
+        stage_put16(stage, o, v);
+        return;
+    }
     StageWriter w;
     sw_init(w, stage, o);
-    if (lit == 0xffffu && cbm == 0u) {                    // all literals: the vector goes out verbatim
-        sw_put_word(w, v.x); sw_put_word(w, v.y);
-        sw_put_word(w, v.z); sw_put_word(w, v.w);
-    } else {
+    {
         // word by word: substitute the count of a run that ends on a non-literal element into its
         // byte (at most one per word: such elements are >= 4 apart), then compact
         const u32 keep = lit | cbm, both = lit & cbm, sub = cbm & ~lit;
@@ -343,17 +371,18 @@ rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
 // ------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------
-// decoder state maps as 8-bit LUTs: bits [2s+1:2s] = next state for state s
-constexpr u32 MAP_ID = 0xE4u;   // 0->0 1->1 2->2 3->3
-constexpr u32 MAP_NE = 0x15u;   // byte differs from previous: 0->1 1->1 2->1 3->0
-constexpr u32 MAP_EQ = 0x39u;   // byte equals previous:       0->1 1->2 2->3 3->0
+// decoder state maps, one byte per state: byte s = next state for state s.  Composition is then a
+// single byte permute (the bytes of b selected by the values of a)
+constexpr u32 MAP_ID = 0x03020100u;   // 0->0 1->1 2->2 3->3
+constexpr u32 MAP_NE = 0x00010101u;   // byte differs from previous: 0->1 1->1 2->1 3->0
+constexpr u32 MAP_EQ = 0x00030201u;   // byte equals previous:       0->1 1->2 2->3 3->0
 
-HC_DEV u32 map_apply(u32 m, u32 s) { return (m >> (2u * s)) & 3u; }
+HC_DEV u32 map_apply(u32 m, u32 s) { return (m >> (8u * s)) & 3u; }
 // first a then b
 HC_DEV u32 map_compose(u32 a, u32 b)
 {
-    return map_apply(b, map_apply(a, 0)) | (map_apply(b, map_apply(a, 1)) << 2) |
-           (map_apply(b, map_apply(a, 2)) << 4) | (map_apply(b, map_apply(a, 3)) << 6);
+    const u32 y = (a | (a >> 4)) & 0x00ff00ffu;       // bytes -> nibbles: the PRMT selector
+    return prmt(b, 0u, (y | (y >> 8)) & 0xffffu);
 }
 struct OpCompose { HC_DEVM u32 operator()(u32 a, u32 b) const { return map_compose(a, b); } };
 
@@ -364,7 +393,7 @@ constexpr u32 DEC_WIN = TPB * 64;   // 16 KiB of output per expansion window
 //   cls8[s][e8]     entering in state s: bits 0..7 = which of the 8 bytes are COUNT bytes (read in
 //                   state 3), bits 8..9 = the state after them
 struct RleDecTables {
-    u8 map8[256];
+    u32 map8[256];
     u16 cls8[4][256];
 };
 
@@ -381,7 +410,7 @@ HC_DEV void rle_dec_init()
     const u32 e8 = threadIdx.x & 255u;
     u32 m = MAP_ID;
     for (u32 k = 0; k < 8u; k++) m = map_compose(m, ((e8 >> k) & 1u) ? MAP_EQ : MAP_NE);
-    t->map8[e8] = (u8)m;
+    t->map8[e8] = m;
     for (u32 s0 = 0; s0 < 4u; s0++) {
         u32 st = s0, cm = 0;
         for (u32 k = 0; k < 8u; k++) {
@@ -429,30 +458,43 @@ HC_DEV u32 rle_masked_byte_sum(const uint4 &v, u32 cm)
 HC_DEV_NOINLINE void rle_dec_scatter(uint4 v, u32 vm, u32 cm, u32 pb, u32 o, u32 w0, u32 w1, u8 *sval, u32 *heads)
 {
     u32 prev = pb;
-#pragma unroll 4
-    for (int k = 0; k < 16; k++) {
-        const u32 b = vec_byte(v, k);
-        if ((vm >> k) & 1u) {
-            const bool is_cnt = (cm >> k) & 1u;
-            const u32 len = is_cnt ? b : 1u, val = is_cnt ? prev : b;
-            if (len && o < w1 && o + len > w0) {
-                const u32 pos = (o > w0 ? o : w0) - w0;
-                sval[pos] = (u8)val;
-                atomic_or_shared(&heads[pos >> 5], 1u << (pos & 31u));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u32 x = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+        const u32 c4 = (cm >> (4 * i)) & 15u, v4 = (vm >> (4 * i)) & 15u;
+        if (c4 == 0u && v4 == 15u && o >= w0 && o + 4u <= w1) {
+            // four literals inside the window
+            const u32 pos = o - w0, sh = pos & 31u;
+            if ((pos & 3u) == 0u) *(u32 *)(sval + pos) = x;
+            else { sval[pos] = (u8)x; sval[pos + 1u] = (u8)(x >> 8); sval[pos + 2u] = (u8)(x >> 16); sval[pos + 3u] = (u8)(x >> 24); }
+            atomic_or_shared(&heads[pos >> 5], 15u << sh);
+            if (sh > 28u) atomic_or_shared(&heads[(pos >> 5) + 1u], 15u >> (32u - sh));
+            o += 4u;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 b = (x >> (8 * k)) & 0xffu;
+                if ((v4 >> k) & 1u) {
+                    const bool is_cnt = (c4 >> k) & 1u;
+                    const u32 len = is_cnt ? b : 1u, val = is_cnt ? prev : b;
+                    if (len && o < w1 && o + len > w0) {
+                        const u32 pos = (o > w0 ? o : w0) - w0;
+                        sval[pos] = (u8)val;
+                        atomic_or_shared(&heads[pos >> 5], 1u << (pos & 31u));
+                    }
+                    o += len;
+                }
+                prev = b;
             }
-            o += len;
         }
-        prev = b;
+        prev = x >> 24;
     }
 }
 
 // the common case of rle_dec_scatter: 16 literals that all lie inside the window, at window offset pos
 HC_DEV_NOINLINE void rle_dec_scatter_literals(uint4 v, u32 pos, u32 sval_addr, u32 *heads)
 {
-    StageWriter w;
-    sw_init(w, sval_addr, pos);
-    sw_put_word(w, v.x); sw_put_word(w, v.y); sw_put_word(w, v.z); sw_put_word(w, v.w);
-    sw_finish(w);
+    stage_put16(sval_addr, pos, v);
     const u32 sh = pos & 31u;
     atomic_or_shared(&heads[pos >> 5], 0xffffu << sh);
     if (sh > 16u) atomic_or_shared(&heads[(pos >> 5) + 1u], 0xffffu >> (32u - sh));
