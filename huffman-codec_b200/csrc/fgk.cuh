@@ -191,6 +191,43 @@ HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, b
     syncwarp();
 }
 
+// fgk_update_plain that also finishes the code of the old path (cursor q) on the way: after the
+// first swap the update continues on another branch of the tree while the code still has to follow
+// the old one.  The two link chases are independent chains, so interleaving them level by level
+// hides the latency of one behind the other.  A further swap (rare) could re-link nodes of the old
+// path, so the chase is completed before any leader search.
+HC_DEV void fgk_update_chase(FgkCtx &c, u32 a, u32 lane, u32 count, u32 q, u32 &hi, u32 &lo, u32 watch, bool &moved)
+{
+    const bool w0 = lane == 0;
+    if (a != c.root) {
+        uint2 n = lds64(a);
+        u32 w1 = lds32(a + 8u);
+        for (;;) {
+            u32 p = n.y;
+            uint2 pn = lds64(p);
+            u32 pw1 = lds32(p + 8u);
+            u32 qn = lds32(q + 4u);                        // unused when q is the root
+            if (w1 == n.x) {
+                for (; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
+                if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved)) {
+                    pn = lds64(p);
+                    pw1 = lds32(p + 8u);
+                }
+            }
+            if (q != c.root) { fgk_code_bit(q, hi, lo); q = qn; }
+            FGK_LEVEL_SYNC();
+            sts32_if(w0, a, n.x + 1u);
+            if (p == c.root) break;
+            a = p;
+            n = pn;
+            w1 = pw1;
+        }
+    }
+    for (; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
+    sts32_if(w0, c.root, count);
+    syncwarp();
+}
+
 // same walk, also collecting the code of the start node in the PRE-update tree
 // (encode precedes update, src/transform.cpp:372-375).  hi:lo must enter as 0x80000000:0.
 // The update path leaves the code path at the first swap; the rest of the old path is then
@@ -209,13 +246,9 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
         if (w1 == n.x) {
             const u32 old_parent = p;
             if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved)) {
-                if (old_parent != c.root) {                // pn still holds the old parent's entry
-                    fgk_code_bit(old_parent, hi, lo);
-                    for (u32 q = pn.y; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
-                }
                 FGK_LEVEL_SYNC();
                 sts32_if(w0, a, n.x + 1u);
-                fgk_update_plain(c, p, lane, count, watch, moved);
+                fgk_update_chase(c, p, lane, count, old_parent, hi, lo, watch, moved);
                 return;
             }
         }
@@ -229,13 +262,9 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
         if (pw1 == pn.x) {
             const u32 old_parent = a;
             if (fgk_leader_swap(c, p, a, pn.x, lane, watch, moved)) {
-                if (old_parent != c.root) {                // n still holds the old parent's entry
-                    fgk_code_bit(old_parent, hi, lo);
-                    for (u32 q = n.y; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
-                }
                 FGK_LEVEL_SYNC();
                 sts32_if(w0, p, pn.x + 1u);
-                fgk_update_plain(c, a, lane, count, watch, moved);
+                fgk_update_chase(c, a, lane, count, old_parent, hi, lo, watch, moved);
                 return;
             }
         }
