@@ -36,17 +36,32 @@ constexpr int FGK_WARPS = HC_FGK_WARPS;  // streams per CTA (4 = one per SM sub-
 constexpr u32 FGK_ROOT = 512;
 constexpr u32 FGK_NSLOT = 514;           // slots 0..512 + one sentinel (weight 0xffffffff)
 constexpr u32 FGK_LEAF_NYT = (256u << 1) | 1u;
+constexpr u32 FGK_D = 9;                         // levels covered by the path table
+constexpr u32 FGK_PT_N = (2u << FGK_D) - 2u;     // 2 + 4 + ... + 2^D entries
+constexpr u32 FGK_NOPATH = 0xffffu;
 
+// PATH TABLE.  pt[(1 << d) - 2 + p] = slot + 1 of the node reached from the root by the d-bit path p
+// (0: no such node), for d = 1..FGK_D; pfx[slot] = d << 12 | p for those nodes (FGK_NOPATH for
+// deeper ones).  With it the nodes of a root->leaf path are found by 32 lanes AT ONCE (one lookup
+// per level) instead of by a chain of dependent loads: decoding reads the next FGK_D code bits and
+// knows every node on the way; encoding takes the code of a leaf straight from pfx; and the
+// update's "does this level need a swap" test runs for all levels of the path in one ballot.
+// The table describes SLOTS, so the most frequent swap (two leaves exchange their symbols) leaves it
+// valid; it is rebuilt (warp-parallel, level by level) after a swap that moves an internal node and
+// after an NYT split.  Deeper levels fall back to the sequential walks.
 struct HC_ALIGNED16 FgkTree {
     uint2 up[FGK_NSLOT];     // {weight, shared address of the parent's up entry}
     u32 down[FGK_NSLOT];     // see above
     u16 slot_of[256];        // leaf slot of a symbol, 0xffff = not yet transmitted
+    u16 pt[FGK_PT_N + 2];
+    u16 pfx[FGK_NSLOT + 2];
     u8 buf[128];             // staging of 128 symbols (one coalesced transfer)
     u8 pad[8];
 };
 
 struct FgkCtx {              // shared addresses, identical in every lane
     u32 up, down, slot_of, buf, root, sentinel, nyt;
+    u32 pt, pfx, lev;        // lev: number of populated levels of pt
 };
 
 HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
@@ -58,7 +73,12 @@ HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
     c.root = c.up + 8u * FGK_ROOT;
     c.sentinel = c.up + 8u * (FGK_ROOT + 1u);
     c.nyt = c.root;
+    c.pt = smem_addr(&t.pt[0]);
+    c.pfx = smem_addr(&t.pfx[0]);
+    c.lev = 0;
     for (u32 i = lane; i < 128u; i += 32) sts32(c.slot_of + 4u * i, 0xffffffffu);
+    for (u32 i = lane; i < (FGK_PT_N + 2u) / 2u; i += 32) sts32(c.pt + 4u * i, 0u);
+    for (u32 i = lane; i < (FGK_NSLOT + 2u) / 2u; i += 32) sts32(c.pfx + 4u * i, 0xffffffffu);
     if (lane == 0) {
         uint2 z; z.x = 0; z.y = 0;
         sts64(c.root, z);
@@ -71,6 +91,41 @@ HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
 
 HC_DEV u32 fgk_down_of(const FgkCtx &c, u32 a) { return c.down + ((a - c.up) >> 1); }   // up address -> down address
 HC_DEV u32 fgk_up_of(const FgkCtx &c, u32 d) { return c.up + ((d - c.down) << 1); }
+
+// Rebuilds the path table from the tree, one level per step, the nodes of a level spread over the
+// lanes.  Called by all lanes after the tree changed shape.
+HC_DEV void fgk_rebuild(FgkCtx &c, u32 lane)
+{
+    syncwarp();                                           // the tree writes of lane 0 are visible
+    for (u32 sl = ((c.nyt - c.up) >> 3) + lane; sl <= FGK_ROOT; sl += 32) sts16(c.pfx + 2u * sl, FGK_NOPATH);
+    syncwarp();
+    u32 lev = 0;
+    for (u32 d = 1; d <= FGK_D; d++) {
+        const u32 base = (1u << d) - 2u, pbase = (1u << (d - 1u)) - 2u;
+        u32 any = 0;
+        for (u32 p = lane; p < (1u << d); p += 32) {
+            const u32 pe = d == 1u ? FGK_ROOT + 1u : lds16(c.pt + 2u * (pbase + (p >> 1)));
+            u32 e = 0;
+            if (pe) {
+                const u32 kd = lds32(c.down + 4u * (pe - 1u));
+                if (!(kd & 1u)) e = ((kd - c.down) >> 2) + (p & 1u) + 1u;     // slot + 1 of the child
+            }
+            sts16(c.pt + 2u * (base + p), e);
+            if (e) sts16(c.pfx + 2u * (e - 1u), (d << 12) | p);
+            any |= e;
+        }
+        syncwarp();
+        if (ballot(any != 0u) == 0u) {
+            // level d is empty (and written as such); clear what an earlier, deeper tree left below
+            for (u32 d2 = d + 1u; d2 <= c.lev; d2++)
+                for (u32 p = lane; p < (1u << d2); p += 32) sts16(c.pt + 2u * ((1u << d2) - 2u + p), 0u);
+            break;
+        }
+        lev = d;
+    }
+    c.lev = lev;
+    syncwarp();
+}
 
 // NYT split (src/huffman.cpp:99-111): the NYT slot n becomes internal with children n-2 (new NYT)
 // and n-1 (leaf of `sym`).  Returns the up address of the new leaf.
@@ -110,11 +165,12 @@ HC_DEV void fgk_code_bit(u32 a, u32 &hi, u32 &lo)
 #define FGK_LEVEL_SYNC() ((void)0)
 #endif
 
+// `sc` (structure changed) is set when the swap moved an internal node.
 // slow path of one level: w[s+1] == w[s].  Finds the block leader (32 slots per ballot) and swaps
 // the subtrees if required (src/huffman.cpp:115-122).  Returns true if a swap happened; a / parent
 // are updated to the slot the node now occupies.  `watch` is the next symbol to be coded: if its
 // leaf moves, *moved is set so that the caller refreshes its prefetched slot.
-HC_DEV bool fgk_leader_swap(FgkCtx &c, u32 &a, u32 &parent, u32 ws, u32 lane, u32 watch, bool &moved)
+HC_DEV bool fgk_leader_swap(FgkCtx &c, u32 &a, u32 &parent, u32 ws, u32 lane, u32 watch, bool &moved, bool &sc)
 {
     u32 l = a + 8u;
     // the common short block: one more plain load decides it without a ballot
@@ -144,6 +200,7 @@ HC_DEV bool fgk_leader_swap(FgkCtx &c, u32 &a, u32 &parent, u32 ws, u32 lane, u3
     }
     if (kl == FGK_LEAF_NYT) c.nyt = a;
     if (ka == FGK_LEAF_NYT) c.nyt = l;
+    if (!(ka & kl & 1u)) sc = true;                       // an internal node moved: the path table is stale
     const u32 wleaf = (watch << 1) | 1u;
     if (ka == wleaf || kl == wleaf) moved = true;
     a = l;
@@ -156,7 +213,7 @@ HC_DEV bool fgk_leader_swap(FgkCtx &c, u32 &a, u32 &parent, u32 ws, u32 lane, u3
 // higher level of the same walk (parents, leaders and probes all have larger slot numbers); the
 // barrier at the end publishes lane 0's writes before the next symbol.  The parent's entry is
 // fetched one level ahead (software pipelining of the dependent shared-memory loads).
-HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, bool &moved)
+HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, bool &moved, bool &sc)
 {
     const bool w0 = lane == 0;
     if (a != c.root) {
@@ -168,7 +225,7 @@ HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, b
             u32 p = n.y;                                   // level A: node a, entry n
             uint2 pn = lds64(p);
             u32 pw1 = lds32(p + 8u);
-            if (w1 == n.x && fgk_leader_swap(c, a, p, n.x, lane, watch, moved)) {
+            if (w1 == n.x && fgk_leader_swap(c, a, p, n.x, lane, watch, moved, sc)) {
                 pn = lds64(p);
                 pw1 = lds32(p + 8u);
             }
@@ -178,7 +235,7 @@ HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, b
             a = pn.y;                                      // level B: node p, entry pn
             n = lds64(a);
             w1 = lds32(a + 8u);
-            if (pw1 == pn.x && fgk_leader_swap(c, p, a, pn.x, lane, watch, moved)) {
+            if (pw1 == pn.x && fgk_leader_swap(c, p, a, pn.x, lane, watch, moved, sc)) {
                 n = lds64(a);
                 w1 = lds32(a + 8u);
             }
@@ -191,12 +248,70 @@ HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, b
     syncwarp();
 }
 
+// FGK update of node a whose path is in the table (pf = its pfx entry): lane j takes the node at
+// depth j + 1, one ballot tells which levels need the leader search.  Levels below the deepest such
+// level are plain increments and done at once; that level is handled by fgk_leader_swap, after which
+// the walk continues from the (possibly new) parent with a fresh table lookup.
+// A1 (optional, first round only): the caller already knows the node of every level (decode found
+// them while resolving the code) -- lane j holds the up address of the node at depth j + 1.
+HC_DEV void fgk_update_fast(FgkCtx &c, u32 a, u32 pf, u32 lane, u32 count, u32 watch, bool &moved, bool have_a1 = false,
+                            u32 A1 = 0)
+{
+    for (;;) {
+        if (pf == FGK_NOPATH) {                           // deeper than the table: sequential walk
+            bool sc = false;
+            fgk_update_plain(c, a, lane, count, watch, moved, sc);
+            if (sc) fgk_rebuild(c, lane);
+            return;
+        }
+        const u32 depth = pf >> 12, path = pf & 0xfffu;
+        const bool valid = lane < depth;
+        u32 A = c.root;                                   // idle lanes: the root never ties (sentinel above it)
+        if (have_a1) {
+            if (valid) A = A1;
+            have_a1 = false;
+        } else if (valid) {
+            A = a;
+            if (lane + 1u < depth) A = c.up - 8u + 8u * lds16(c.pt + 2u * ((2u << lane) - 2u + (path >> (depth - 1u - lane))));
+        }
+        const u32 W = lds32(A), w1 = lds32(A + 8u);
+        const u32 tm = ballot(valid && w1 == W);
+        FGK_LEVEL_SYNC();
+        if (tm == 0u) {
+            sts32_if(valid, A, W + 1u);
+            sts32_if(lane == 0, c.root, count);
+            syncwarp();
+            return;
+        }
+        const u32 k0 = 31u - (u32)clz(tm);                // deepest level with a tie
+        sts32_if(valid && lane > k0, A, W + 1u);          // plain levels below it
+        u32 ak = shfl(A, (int)k0);
+        const u32 wk = shfl(W, (int)k0);
+        u32 parent = shfl(A, (int)(k0 ? k0 - 1u : 0u));
+        if (k0 == 0u) parent = c.root;
+        bool sc = false;
+        fgk_leader_swap(c, ak, parent, wk, lane, watch, moved, sc);
+        FGK_LEVEL_SYNC();
+        sts32_if(lane == 0, ak, wk + 1u);
+        if (parent == c.root) {
+            sts32_if(lane == 0, c.root, count);
+            syncwarp();
+            if (sc) fgk_rebuild(c, lane);
+            return;
+        }
+        syncwarp();
+        if (sc) fgk_rebuild(c, lane);
+        a = parent;
+        pf = lds16(c.pfx + ((a - c.up) >> 2));            // 2 bytes per slot, 8 bytes per up entry
+    }
+}
+
 // fgk_update_plain that also finishes the code of the old path (cursor q) on the way: after the
 // first swap the update continues on another branch of the tree while the code still has to follow
 // the old one.  The two link chases are independent chains, so interleaving them level by level
 // hides the latency of one behind the other.  A further swap (rare) could re-link nodes of the old
 // path, so the chase is completed before any leader search.
-HC_DEV void fgk_update_chase(FgkCtx &c, u32 a, u32 lane, u32 count, u32 q, u32 &hi, u32 &lo, u32 watch, bool &moved)
+HC_DEV void fgk_update_chase(FgkCtx &c, u32 a, u32 lane, u32 count, u32 q, u32 &hi, u32 &lo, u32 watch, bool &moved, bool &sc)
 {
     const bool w0 = lane == 0;
     if (a != c.root) {
@@ -209,7 +324,7 @@ HC_DEV void fgk_update_chase(FgkCtx &c, u32 a, u32 lane, u32 count, u32 q, u32 &
             u32 qn = lds32(q + 4u);                        // unused when q is the root
             if (w1 == n.x) {
                 for (; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
-                if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved)) {
+                if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved, sc)) {
                     pn = lds64(p);
                     pw1 = lds32(p + 8u);
                 }
@@ -232,7 +347,7 @@ HC_DEV void fgk_update_chase(FgkCtx &c, u32 a, u32 lane, u32 count, u32 q, u32 &
 // (encode precedes update, src/transform.cpp:372-375).  hi:lo must enter as 0x80000000:0.
 // The update path leaves the code path at the first swap; the rest of the old path is then
 // finished by a pure parent chase (safe: the first swap never re-parents an old-path node).
-HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u32 &lo, u32 watch, bool &moved)
+HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u32 &lo, u32 watch, bool &moved, bool &sc)
 {
     const bool w0 = lane == 0;
     uint2 n = lds64(a);                       // a is a leaf: never the root
@@ -245,10 +360,10 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
         fgk_code_bit(a, hi, lo);
         if (w1 == n.x) {
             const u32 old_parent = p;
-            if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved)) {
+            if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved, sc)) {
                 FGK_LEVEL_SYNC();
                 sts32_if(w0, a, n.x + 1u);
-                fgk_update_chase(c, p, lane, count, old_parent, hi, lo, watch, moved);
+                fgk_update_chase(c, p, lane, count, old_parent, hi, lo, watch, moved, sc);
                 return;
             }
         }
@@ -261,10 +376,10 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
         fgk_code_bit(p, hi, lo);
         if (pw1 == pn.x) {
             const u32 old_parent = a;
-            if (fgk_leader_swap(c, p, a, pn.x, lane, watch, moved)) {
+            if (fgk_leader_swap(c, p, a, pn.x, lane, watch, moved, sc)) {
                 FGK_LEVEL_SYNC();
                 sts32_if(w0, p, pn.x + 1u);
-                fgk_update_chase(c, a, lane, count, old_parent, hi, lo, watch, moved);
+                fgk_update_chase(c, a, lane, count, old_parent, hi, lo, watch, moved, sc);
                 return;
             }
         }
@@ -274,6 +389,37 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
     }
     sts32_if(w0, c.root, count);
     syncwarp();
+}
+
+// The trees of the resident CTAs no longer hold the whole batch at once, so streams are started in
+// order of decreasing length class (counting sort, 4 classes per octave): the long ones first, the
+// short ones fill the slots they free.  One CTA; the order inside a class is arbitrary (it only
+// affects scheduling, never the output).
+HC_KERNEL HC_LAUNCH_BOUNDS(1024, 1)
+fgk_order_kernel(const u64 *HC_RESTRICT len, u32 nf, u32 *HC_RESTRICT order)
+{
+    HC_SHARED u32 hist[256];
+    const u32 tid = threadIdx.x;
+    if (tid < 256u) hist[tid] = 0;
+    syncthreads();
+    for (u32 f = tid; f < nf; f += blockDim.x) {
+        const u64 v = len[f];
+        u32 cl = 0;
+        if (v) { const u32 lg = 63u - (u32)clzll(v); cl = 4u * lg + (u32)((lg >= 2u ? v >> (lg - 2u) : v << (2u - lg)) & 3u); }
+        atomic_add(&hist[cl > 255u ? 255u : cl], 1u);
+    }
+    syncthreads();
+    if (tid == 0) {
+        u32 acc = 0;
+        for (int b = 255; b >= 0; b--) { const u32 h = hist[b]; hist[b] = acc; acc += h; }
+    }
+    syncthreads();
+    for (u32 f = tid; f < nf; f += blockDim.x) {
+        const u64 v = len[f];
+        u32 cl = 0;
+        if (v) { const u32 lg = 63u - (u32)clzll(v); cl = 4u * lg + (u32)((lg >= 2u ? v >> (lg - 2u) : v << (2u - lg)) & 3u); }
+        order[atomic_add(&hist[cl > 255u ? 255u : cl], 1u)] = f;
+    }
 }
 
 // MSB-first bit writer: one 32-bit word per lane, 128-byte coalesced flushes
@@ -346,13 +492,15 @@ HC_DEV u64 bw_finish(BitWriter &b, u32 lane)
 HC_KERNEL HC_LAUNCH_BOUNDS(FGK_WARPS * 32, 1)
 fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, const u64 *HC_RESTRICT sym_len,
                   const u8 *HC_RESTRICT flags, u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off,
-                  const u64 *HC_RESTRICT out_cap, u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
+                  const u64 *HC_RESTRICT out_cap, u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf,
+                  const u32 *HC_RESTRICT order)
 {
     HC_SHARED FgkTree trees[FGK_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 f = blockIdx.x * FGK_WARPS + wid;
-    if (f >= nf) return;
+    const u32 fi = blockIdx.x * FGK_WARPS + wid;
+    if (fi >= nf) return;
+    const u32 f = order ? order[fi] : fi;               // longest streams first (fgk_order_kernel)
     FgkCtx c;
     fgk_init(c, trees[wid], lane);
 
@@ -383,19 +531,31 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
             const u32 yn = lds8(c.buf + ((i + 1u) & 127u));
             u32 slot_n = lds16(c.slot_of + 2u * yn);
             bool moved = false;
-            u32 hi = 0x80000000u, lo = 0u;
             count++;
             if (slot == 0xffffu) {
                 // not yet transmitted: NYT code followed by the 8 raw bits (src/huffman.cpp:42-51)
+                u32 hi = 0x80000000u, lo = 0u;
                 for (u32 p = c.nyt; p != c.root; p = lds32(p + 4u)) fgk_code_bit(p, hi, lo);
                 if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
                 bw_put(bw, y, 8, lane);
                 const u32 leaf = fgk_split(c, y, lane);
-                fgk_update_plain(c, leaf, lane, count, yn, moved);
+                bool sc = false;
+                fgk_update_plain(c, leaf, lane, count, yn, moved, sc);
+                fgk_rebuild(c, lane);                     // the split changed the shape of the tree
                 if (yn == y) moved = true;
             } else {
-                fgk_update_coding(c, c.up + 8u * slot, lane, count, hi, lo, yn, moved);
-                if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
+                const u32 pf = lds16(c.pfx + 2u * slot);
+                if (pf != FGK_NOPATH) {
+                    // the code of a leaf is its path (encode precedes update, src/transform.cpp:372-375)
+                    bw_put(bw, pf & 0xfffu, pf >> 12, lane);
+                    fgk_update_fast(c, c.up + 8u * slot, pf, lane, count, yn, moved);
+                } else {
+                    u32 hi = 0x80000000u, lo = 0u;
+                    bool sc = false;
+                    fgk_update_coding(c, c.up + 8u * slot, lane, count, hi, lo, yn, moved, sc);
+                    if (sc) fgk_rebuild(c, lane);
+                    if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
+                }
             }
             if (moved) slot_n = lds16(c.slot_of + 2u * yn);
             y = yn;
@@ -465,13 +625,15 @@ HC_DEV u32 br_get(BitReader &r, u32 d, u32 lane)   // 1..32 bits; caller checks 
 HC_KERNEL HC_LAUNCH_BOUNDS(FGK_WARPS * 32, 1)
 fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, const u64 *HC_RESTRICT sym_cap,
-                  u64 *HC_RESTRICT sym_len, u8 *HC_RESTRICT flags, i32 *HC_RESTRICT status, u32 nf)
+                  u64 *HC_RESTRICT sym_len, u8 *HC_RESTRICT flags, i32 *HC_RESTRICT status, u32 nf,
+                  const u32 *HC_RESTRICT order)
 {
     HC_SHARED FgkTree trees[FGK_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 f = blockIdx.x * FGK_WARPS + wid;
-    if (f >= nf) return;
+    const u32 fi = blockIdx.x * FGK_WARPS + wid;
+    if (fi >= nf) return;
+    const u32 f = order ? order[fi] : fi;               // longest streams first (fgk_order_kernel)
     FgkCtx c;
     fgk_init(c, trees[wid], lane);
 
@@ -499,61 +661,84 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     i32 err = 0;
     u32 count = 0;
     for (u64 i = 0; i < m; i++) {
-        // walk down on a private copy of the window's top 32 bits, consume them afterwards.  Lane j
-        // remembers the node reached after j+1 steps: the walk visits exactly the nodes the update
-        // will increment, so the update needs no second (leaf->root) chase.
-        u32 d = root_down, k = lds32(d), t = (u32)(br.win >> 32), depth = 0, dk = 0;
-        // fast walk: no length check inside the loop.  Past 32 steps `t` only supplies zeros, i.e. the
-        // walk keeps taking (valid) left children and still ends at a leaf; such a symbol is redone below.
-        while (!(k & 1u)) {
-            d = k + ((t >> 29) & 4u);
-            if (lane == depth) dk = d;
-            t <<= 1;
-            depth++;
-            k = lds32(d);
-        }
-        if (depth > 32u) {
-            // code longer than 32 bits (very deep tree): exact walk, 32 bits at a time
-            d = root_down; k = lds32(d); t = (u32)(br.win >> 32); depth = 0;
-            u32 len = 0;
+        // The path table resolves the next FGK_D code bits in one step: lane j looks up the node that
+        // the first j + 1 bits lead to; the shallowest leaf among them ends the code.
+        u32 t = (u32)(br.win >> 32), depth = 0, k = 0, d = 0, dk = 0, aleaf = 0;
+        u32 e = 0, kj = 0;
+        if (lane < FGK_D) e = lds16(c.pt + 2u * ((2u << lane) - 2u + (t >> (31u - lane))));
+        if (e) kj = lds32(c.down + 4u * (e - 1u));
+        const u32 leafm = ballot(e != 0u && (kj & 1u));
+        const bool via_table = leafm != 0u;
+        if (via_table) {
+            depth = (u32)ffs(leafm);
+            k = shfl(kj, (int)(depth - 1u));
+            aleaf = c.up - 8u + 8u * shfl(e, (int)(depth - 1u));
+            if (br.avail < depth) { err = 9; break; }    // ran out of bits inside a code
+        } else {
+            // the root is still a leaf, or the code is longer than the table: walk down on a private
+            // copy of the window's top 32 bits, consume them afterwards.  Lane j remembers the node
+            // reached after j+1 steps.  No length check inside the loop: past 32 steps `t` only supplies
+            // zeros, i.e. the walk keeps taking (valid) left children and still ends at a leaf; such a
+            // symbol is redone below.
+            d = root_down; k = lds32(d);
             while (!(k & 1u)) {
-                if (len == 32u) {
-                    if (br.avail < 32u) { err = 9; break; }
-                    br_skip(br, 32, lane);
-                    t = (u32)(br.win >> 32);
-                    len = 0;
-                }
                 d = k + ((t >> 29) & 4u);
+                if (lane == depth) dk = d;
                 t <<= 1;
-                len++;
                 depth++;
                 k = lds32(d);
             }
-            if (err) break;
-            if (len) {
-                if (br.avail < len) { err = 9; break; }
-                br_skip(br, len, lane);
+            if (depth > 32u) {
+                // code longer than 32 bits (very deep tree): exact walk, 32 bits at a time
+                d = root_down; k = lds32(d); t = (u32)(br.win >> 32); depth = 0;
+                u32 len = 0;
+                while (!(k & 1u)) {
+                    if (len == 32u) {
+                        if (br.avail < 32u) { err = 9; break; }
+                        br_skip(br, 32, lane);
+                        t = (u32)(br.win >> 32);
+                        len = 0;
+                    }
+                    d = k + ((t >> 29) & 4u);
+                    t <<= 1;
+                    len++;
+                    depth++;
+                    k = lds32(d);
+                }
+                if (err) break;
+                if (len) {
+                    if (br.avail < len) { err = 9; break; }
+                    br_skip(br, len, lane);
+                }
+            } else if (depth) {
+                if (br.avail < depth) { err = 9; break; }
             }
-        } else if (depth) {
-            if (br.avail < depth) { err = 9; break; }    // ran out of bits inside a code
-            br_skip(br, depth, lane);
         }
+        const u32 pf_leaf = (depth << 12) | (depth ? (u32)(br.win >> 32) >> ((32u - depth) & 31u) : 0u);
+        if (depth && depth <= 32u) br_skip(br, depth, lane);
         count++;
         u32 y;
-        bool moved = false;
+        bool moved = false, sc = false;
         if (k == FGK_LEAF_NYT) {
             if (br.avail < 8u) { err = 9; break; }
             y = br_get(br, 8, lane);
             // a raw symbol that is already in the tree is still decoded as that symbol
             // (src/huffman.cpp:74-86); the update then starts from its existing leaf
             const u32 ex = lds16(c.slot_of + 2u * y);
-            const u32 a = ex == 0xffffu ? fgk_split(c, y, lane) : c.up + 8u * ex;
             if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
-            fgk_update_plain(c, a, lane, count, 0x1ffu, moved);          // ends with a warp barrier
+            if (ex == 0xffffu) {
+                const u32 a = fgk_split(c, y, lane);
+                fgk_update_plain(c, a, lane, count, 0x1ffu, moved, sc);  // ends with a warp barrier
+                fgk_rebuild(c, lane);                                    // the split changed the shape of the tree
+            } else {
+                fgk_update_fast(c, c.up + 8u * ex, lds16(c.pfx + 2u * ex), lane, count, 0x1ffu, moved);
+            }
         } else {
             y = k >> 1;
             if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
-            if (depth <= 32u) {
+            if (via_table) {
+                fgk_update_fast(c, aleaf, pf_leaf, lane, count, 0x1ffu, moved, true, c.up - 8u + 8u * e);
+            } else if (depth <= 32u) {
                 // all levels at once, one lane per level (lane depth-1 = the leaf): a level whose next
                 // slot carries the same weight needs leader search / swap and everything above it may
                 // move, so the sequential walk takes over from the deepest such level.
@@ -569,10 +754,12 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                 } else {
                     const u32 k0 = 31u - (u32)clz(tm);                   // deepest level with a tie
                     sts32_if(valid && lane > k0, A, W + 1u);             // plain levels below it
-                    fgk_update_plain(c, shfl(A, (int)k0), lane, count, 0x1ffu, moved);
+                    fgk_update_plain(c, shfl(A, (int)k0), lane, count, 0x1ffu, moved, sc);
+                    if (sc) fgk_rebuild(c, lane);
                 }
             } else {
-                fgk_update_plain(c, fgk_up_of(c, d), lane, count, 0x1ffu, moved);
+                fgk_update_plain(c, fgk_up_of(c, d), lane, count, 0x1ffu, moved, sc);
+                if (sc) fgk_rebuild(c, lane);
             }
         }
         if ((i & 127u) == 127u) {

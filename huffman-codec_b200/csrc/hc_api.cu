@@ -435,15 +435,43 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
     return 0;
 }
 
+// order_ws: nf u32 of device scratch for the longest-first start order, or NULL (file order)
+static int fgk_encode_launch(const uint8_t *sym, const uint64_t *sym_off, const uint64_t *sym_len, const uint8_t *flags,
+                             uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_len,
+                             int32_t *status, uint32_t nf, u32 *order_ws, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    if (order_ws) {
+        HC_LAUNCH(fgk_order_kernel, dim3(1), dim3(1024), 0, stream, sym_len, nf, order_ws);
+        HC_CHECK_LAUNCH();
+    }
+    HC_LAUNCH(fgk_encode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, sym,
+              sym_off, sym_len, flags, out, out_off, out_cap, out_len, status, nf, (const u32 *)order_ws);
+    HC_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int hc_fgk_encode_batch(const uint8_t *sym, const uint64_t *sym_off, const uint64_t *sym_len,
                                    const uint8_t *flags,
                                    uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
                                    uint64_t *out_len, int32_t *status,
                                    uint32_t nf, hc_stream_t stream)
 {
+    return fgk_encode_launch(sym, sym_off, sym_len, flags, out, out_off, out_cap, out_len, status, nf, nullptr, stream);
+}
+
+static int fgk_decode_launch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                             uint8_t *sym, const uint64_t *sym_off, const uint64_t *sym_cap,
+                             uint64_t *sym_len, uint8_t *flags, int32_t *status,
+                             uint32_t nf, u32 *order_ws, hc_stream_t stream)
+{
     if (nf == 0) return 0;
-    HC_LAUNCH(fgk_encode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, sym,
-              sym_off, sym_len, flags, out, out_off, out_cap, out_len, status, nf);
+    if (order_ws) {
+        HC_LAUNCH(fgk_order_kernel, dim3(1), dim3(1024), 0, stream, in_len, nf, order_ws);   // compressed bytes ~ work
+        HC_CHECK_LAUNCH();
+    }
+    HC_LAUNCH(fgk_decode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, in,
+              in_off, in_len, sym, sym_off, sym_cap, sym_len, flags, status, nf, (const u32 *)order_ws);
     HC_CHECK_LAUNCH();
     return 0;
 }
@@ -453,11 +481,7 @@ extern "C" int hc_fgk_decode_batch(const uint8_t *in, const uint64_t *in_off, co
                                    uint64_t *sym_len, uint8_t *flags, int32_t *status,
                                    uint32_t nf, hc_stream_t stream)
 {
-    if (nf == 0) return 0;
-    HC_LAUNCH(fgk_decode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, in,
-              in_off, in_len, sym, sym_off, sym_cap, sym_len, flags, status, nf);
-    HC_CHECK_LAUNCH();
-    return 0;
+    return fgk_decode_launch(in, in_off, in_len, sym, sym_off, sym_cap, sym_len, flags, status, nf, nullptr, stream);
 }
 
 extern "C" int hc_offsets_from_lens(const uint64_t *len, uint64_t *out_off, uint64_t *total,
@@ -521,7 +545,7 @@ struct HostBuf {
 struct hc_codec {
     int device = 0;
     cudaStream_t stream = nullptr;
-    DevBuf in, a, b, out, tab, ws;      // raw input, stage buffers, strided output, tables, scratch
+    DevBuf in, a, b, out, tab, ws, ord;  // raw input, stage buffers, strided output, tables, scratch, FGK start order
     HostBuf htab;
     bool timing = false;
     cudaEvent_t ev[HC_MAX_STAGES + 1];
@@ -573,7 +597,7 @@ extern "C" void hc_codec_destroy(hc_codec *c)
     c->kids.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release();
+    c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release(); c->ord.release();
     c->htab.release();
     if (c->ev_ready) for (int i = 0; i <= HC_MAX_STAGES; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
@@ -669,8 +693,9 @@ extern "C" int hc_compress_device(hc_codec *c, const uint8_t *d_in, const uint64
     HC_LAUNCH(mask_len_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, t.u64_at(T_LEN_B), (const i32 *)t.i32_at(T_ST0),
               (const i32 *)st1, nf);
     HC_CHECK_LAUNCH();
-    HC_TRY(hc_fgk_encode_batch((const u8 *)c->b.p, t.u64_at(T_OFF_B), t.u64_at(T_LEN_B), t.u8_at(T_FLAGS), d_out, d_out_off,
-                               d_out_cap, d_out_len, t.i32_at(T_ST2), nf, s));
+    HC_TRY(c->ord.ensure((size_t)nf * 4));
+    HC_TRY(fgk_encode_launch((const u8 *)c->b.p, t.u64_at(T_OFF_B), t.u64_at(T_LEN_B), t.u8_at(T_FLAGS), d_out, d_out_off,
+                               d_out_cap, d_out_len, t.i32_at(T_ST2), nf, (u32 *)c->ord.p, s));
     stage_mark(c, "fgk_encode");
     HC_LAUNCH(merge_status_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, (const i32 *)t.i32_at(T_ST0), (const i32 *)st1,
               (const i32 *)t.i32_at(T_ST2), d_status, d_out_len, nf);
@@ -690,8 +715,9 @@ static int dec_fgk(hc_codec *c, const uint8_t *d_in, const uint64_t *d_in_off, c
     HC_TRY(c->a.ensure((size_t)stride_a * nf));
     HC_LAUNCH(strided_offsets_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, t.u64_at(T_OFF_A), t.u64_at(T_CAP_A), stride_a, nf);
     HC_CHECK_LAUNCH();
-    HC_TRY(hc_fgk_decode_batch(d_in, d_in_off, d_in_len, (u8 *)c->a.p, t.u64_at(T_OFF_A), t.u64_at(T_CAP_A), t.u64_at(T_LEN_A),
-                               t.u8_at(T_FLAGS), t.i32_at(T_ST0), nf, s));
+    HC_TRY(c->ord.ensure((size_t)nf * 4));
+    HC_TRY(fgk_decode_launch(d_in, d_in_off, d_in_len, (u8 *)c->a.p, t.u64_at(T_OFF_A), t.u64_at(T_CAP_A), t.u64_at(T_LEN_A),
+                               t.u8_at(T_FLAGS), t.i32_at(T_ST0), nf, (u32 *)c->ord.p, s));
     stage_mark(c, "fgk_decode");
     HC_LAUNCH(decompress_split_kernel, dim3(blocks_for(nf)), dim3(256), 0, s, (const u64 *)t.u64_at(T_LEN_A),
               (const u8 *)t.u8_at(T_FLAGS), (const i32 *)t.i32_at(T_ST0), t.u64_at(T_LEN_P), t.u64_at(T_LEN_AD), nf);
