@@ -127,6 +127,73 @@ HC_DEV void fgk_rebuild(FgkCtx &c, u32 lane)
     syncwarp();
 }
 
+// After slots x and y exchanged their subtrees only the table entries BELOW them change (the slots
+// keep their own paths).  px / py = their pfx entries (FGK_NOPATH: that slot lies deeper than the
+// table, nothing below it is listed).  First every node listed below either slot loses its path,
+// then both ranges are re-derived level by level.
+HC_DEV void fgk_rebuild_pair(FgkCtx &c, u32 px, u32 py, u32 lane)
+{
+    syncwarp();                                           // the tree writes of lane 0 are visible
+#pragma unroll 1
+    for (u32 side = 0; side < 2u; side++) {
+        const u32 pf = side ? py : px;
+        if (pf == FGK_NOPATH) continue;
+        const u32 depth = pf >> 12, path = pf & 0xfffu;
+        for (u32 d = depth + 1u; d <= FGK_D; d++) {
+            const u32 n = 1u << (d - depth), base = (1u << d) - 2u + (path << (d - depth));
+            for (u32 i = lane; i < n; i += 32) {
+                const u32 e = lds16(c.pt + 2u * (base + i));
+                if (e) sts16(c.pfx + 2u * (e - 1u), FGK_NOPATH);
+            }
+        }
+    }
+    syncwarp();
+    u32 lev = c.lev;
+#pragma unroll 1
+    for (u32 side = 0; side < 2u; side++) {
+        const u32 pf = side ? py : px;
+        if (pf == FGK_NOPATH) continue;
+        const u32 depth = pf >> 12, path = pf & 0xfffu;
+        for (u32 d = depth + 1u; d <= FGK_D; d++) {
+            const u32 n = 1u << (d - depth), p0 = path << (d - depth);
+            const u32 base = (1u << d) - 2u, pbase = (1u << (d - 1u)) - 2u;
+            u32 any = 0;
+            for (u32 i = lane; i < n; i += 32) {
+                const u32 p = p0 + i;
+                const u32 pe = lds16(c.pt + 2u * (pbase + (p >> 1)));
+                u32 e = 0;
+                if (pe) {
+                    const u32 kd = lds32(c.down + 4u * (pe - 1u));
+                    if (!(kd & 1u)) e = ((kd - c.down) >> 2) + (p & 1u) + 1u;
+                }
+                sts16(c.pt + 2u * (base + p), e);
+                if (e) sts16(c.pfx + 2u * (e - 1u), (d << 12) | p);
+                any |= e;
+            }
+            syncwarp();
+            if (ballot(any != 0u) && d > lev) lev = d;
+        }
+    }
+    c.lev = lev;
+}
+
+// table entries of the two slots created by an NYT split of slot n (up address); pn = pfx of n
+// before the split, or depth 0 for the root
+HC_DEV void fgk_table_split(FgkCtx &c, u32 n, u32 pn, u32 lane)
+{
+    if (pn == FGK_NOPATH) return;                         // deeper than the table: the new slots stay unlisted
+    const u32 depth = pn >> 12, path = pn & 0xfffu;
+    if (depth >= FGK_D) return;
+    const u32 d = depth + 1u, sl = (n - c.up) >> 3;       // children: slots sl-2 (bit 0) and sl-1 (bit 1)
+    if (lane < 2u) {
+        const u32 p = (path << 1) | lane, child = sl - 2u + lane;
+        sts16(c.pt + 2u * ((1u << d) - 2u + p), child + 1u);
+        sts16(c.pfx + 2u * child, (d << 12) | p);
+    }
+    if (d > c.lev) c.lev = d;
+    syncwarp();
+}
+
 // NYT split (src/huffman.cpp:99-111): the NYT slot n becomes internal with children n-2 (new NYT)
 // and n-1 (leaf of `sym`).  Returns the up address of the new leaf.
 HC_DEV u32 fgk_split(FgkCtx &c, u32 sym, u32 lane)
@@ -293,14 +360,18 @@ HC_DEV void fgk_update_fast(FgkCtx &c, u32 a, u32 pf, u32 lane, u32 count, u32 w
         fgk_leader_swap(c, ak, parent, wk, lane, watch, moved, sc);
         FGK_LEVEL_SYNC();
         sts32_if(lane == 0, ak, wk + 1u);
+        if (sc) {
+            // an internal node moved: only the entries below the two slots change.  The old slot is
+            // the node of level k0 of this path; ak is now the leader's slot
+            const u32 pf_a = ((k0 + 1u) << 12) | (path >> (depth - 1u - k0));
+            fgk_rebuild_pair(c, pf_a, lds16(c.pfx + ((ak - c.up) >> 2)), lane);
+        }
         if (parent == c.root) {
             sts32_if(lane == 0, c.root, count);
             syncwarp();
-            if (sc) fgk_rebuild(c, lane);
             return;
         }
         syncwarp();
-        if (sc) fgk_rebuild(c, lane);
         a = parent;
         pf = lds16(c.pfx + ((a - c.up) >> 2));            // 2 bytes per slot, 8 bytes per up entry
     }
@@ -538,10 +609,12 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
                 for (u32 p = c.nyt; p != c.root; p = lds32(p + 4u)) fgk_code_bit(p, hi, lo);
                 if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
                 bw_put(bw, y, 8, lane);
+                const u32 nsl = c.nyt, npf = nsl == c.root ? 0u : lds16(c.pfx + ((nsl - c.up) >> 2));
                 const u32 leaf = fgk_split(c, y, lane);
+                fgk_table_split(c, nsl, npf, lane);
                 bool sc = false;
                 fgk_update_plain(c, leaf, lane, count, yn, moved, sc);
-                fgk_rebuild(c, lane);                     // the split changed the shape of the tree
+                if (sc) fgk_rebuild(c, lane);
                 if (yn == y) moved = true;
             } else {
                 const u32 pf = lds16(c.pfx + 2u * slot);
@@ -727,9 +800,11 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             const u32 ex = lds16(c.slot_of + 2u * y);
             if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
             if (ex == 0xffffu) {
+                const u32 nsl = c.nyt, npf = nsl == c.root ? 0u : lds16(c.pfx + ((nsl - c.up) >> 2));
                 const u32 a = fgk_split(c, y, lane);
+                fgk_table_split(c, nsl, npf, lane);
                 fgk_update_plain(c, a, lane, count, 0x1ffu, moved, sc);  // ends with a warp barrier
-                fgk_rebuild(c, lane);                                    // the split changed the shape of the tree
+                if (sc) fgk_rebuild(c, lane);
             } else {
                 fgk_update_fast(c, c.up + 8u * ex, lds16(c.pfx + 2u * ex), lane, count, 0x1ffu, moved);
             }
