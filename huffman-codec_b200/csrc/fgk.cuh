@@ -787,7 +787,7 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                 if (br.avail < depth) { err = 9; break; }
             }
         }
-        const u32 pf_leaf = (depth << 12) | (depth ? (u32)(br.win >> 32) >> ((32u - depth) & 31u) : 0u);
+        const u32 pf_leaf = (depth << 12) | (t >> ((32u - depth) & 31u));   // used on the table path only (t intact, depth >= 1)
         if (depth && depth <= 32u) br_skip(br, depth, lane);
         count++;
         u32 y;

@@ -815,7 +815,7 @@ struct AsyncFree {   // stream-ordered scratch released on every exit path
 };
 
 // ---- group pipelines -----------------------------------------------------------------------------
-// The host-level calls split the batch into up to HC_MAX_GROUPS contiguous groups of files, each with
+// The host-level calls split large batches into up to HC_MAX_GROUPS contiguous groups of files, each with
 // its own stream and buffers (a child codec).  Host<->device copies of one group overlap the kernels
 // of the others, and the FGK kernels of all groups are resident together -- that stage is bound by the
 // latency of its longest stream, so running the groups one after another would multiply its time.
@@ -834,7 +834,12 @@ static int ensure_kids(hc_codec *c, u32 g)
 
 static u32 group_count(u32 nf)
 {
-    u32 g = nf / 64;
+    const char *env = getenv("HC_GROUPS");                 // tests / experiments: force the group count
+    const int forced = env ? atoi(env) : 0;
+    // a group should still fill the FGK stage on its own (2960 resident streams + the short ones that
+    // follow them): measured on C3, 4096 files in 1 group 4.84 GB/s end to end, in 8 groups 4.19 GB/s
+    u32 g = forced > 0 ? (u32)forced : nf / 4096;
+    if (g > nf) g = nf;
     return g < 1 ? 1 : (g > HC_MAX_GROUPS ? HC_MAX_GROUPS : g);
 }
 

@@ -220,10 +220,12 @@ def test_cli_matches_reference_cli(samples, golden):
             assert r.stderr.decode() == c["stderr"].replace("$TMP", tmp), c
 
 
-def test_many_files_cross_group_pipeline(codec, oracle):
-    """> 128 files: the host-level calls split the batch into several group pipelines (own stream and
-    buffers each); offsets, lengths and statuses must still line up with the file order."""
+def test_many_files_cross_group_pipeline(codec, oracle, monkeypatch):
+    """The host-level calls split large batches into several group pipelines (own stream and buffers
+    each; by default one per 4096 files, forced to 3 here); offsets, lengths and statuses must still
+    line up with the file order."""
     cd, name = codec
+    monkeypatch.setenv("HC_GROUPS", "3")
     rng = np.random.default_rng(5)
     nfile = 200
     files, widths = [], []
