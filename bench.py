@@ -212,7 +212,18 @@ def run_ours(args):
 
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout at the first collective; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     L = hc_b200.lib()
     cd = hc_b200.Codec(local, L)
     stream = torch.cuda.ExternalStream(L.hc_codec_stream(cd.h), device=torch.device("cuda", local))
