@@ -321,8 +321,10 @@ HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, b
 // the walk continues from the (possibly new) parent with a fresh table lookup.
 // A1 (optional, first round only): the caller already knows the node of every level (decode found
 // them while resolving the code) -- lane j holds the up address of the node at depth j + 1.
+// W1 / W1n: the weights of that node and of the slot after it, fetched by the caller together with
+// its own lookups (lanes without a level hold the root, which never ties).
 HC_DEV void fgk_update_fast(FgkCtx &c, u32 a, u32 pf, u32 lane, u32 count, u32 watch, bool &moved, bool have_a1 = false,
-                            u32 A1 = 0)
+                            u32 A1 = 0, u32 W1 = 0, u32 W1n = 0)
 {
     for (;;) {
         if (pf == FGK_NOPATH) {                           // deeper than the table: sequential walk
@@ -334,14 +336,18 @@ HC_DEV void fgk_update_fast(FgkCtx &c, u32 a, u32 pf, u32 lane, u32 count, u32 w
         const u32 depth = pf >> 12, path = pf & 0xfffu;
         const bool valid = lane < depth;
         u32 A = c.root;                                   // idle lanes: the root never ties (sentinel above it)
+        u32 W, w1;
         if (have_a1) {
-            if (valid) A = A1;
+            A = A1; W = W1; w1 = W1n;
             have_a1 = false;
-        } else if (valid) {
-            A = a;
-            if (lane + 1u < depth) A = c.up - 8u + 8u * lds16(c.pt + 2u * ((2u << lane) - 2u + (path >> (depth - 1u - lane))));
+        } else {
+            if (valid) {
+                A = a;
+                if (lane + 1u < depth) A = c.up - 8u + 8u * lds16(c.pt + 2u * ((2u << lane) - 2u + (path >> (depth - 1u - lane))));
+            }
+            W = lds32(A);
+            w1 = lds32(A + 8u);
         }
-        const u32 W = lds32(A), w1 = lds32(A + 8u);
         const u32 tm = ballot(valid && w1 == W);
         FGK_LEVEL_SYNC();
         if (tm == 0u) {
@@ -740,6 +746,10 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
         u32 e = 0, kj = 0;
         if (lane < FGK_D) e = lds16(c.pt + 2u * ((2u << lane) - 2u + (t >> (31u - lane))));
         if (e) kj = lds32(c.down + 4u * (e - 1u));
+        // the update's first question ("does a level need a leader search?") rides on the same round
+        // of loads: weights of the node and of the slot after it (no node: the root, which never ties)
+        const u32 A1 = e ? c.up - 8u + 8u * e : c.root;
+        const u32 W1 = lds32(A1), W1n = lds32(A1 + 8u);
         const u32 leafm = ballot(e != 0u && (kj & 1u));
         const bool via_table = leafm != 0u;
         if (via_table) {
@@ -812,7 +822,7 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
             y = k >> 1;
             if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
             if (via_table) {
-                fgk_update_fast(c, aleaf, pf_leaf, lane, count, 0x1ffu, moved, true, c.up - 8u + 8u * e);
+                fgk_update_fast(c, aleaf, pf_leaf, lane, count, 0x1ffu, moved, true, A1, W1, W1n);
             } else if (depth <= 32u) {
                 // all levels at once, one lane per level (lane depth-1 = the leaf): a level whose next
                 // slot carries the same weight needs leader search / swap and everything above it may
