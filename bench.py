@@ -78,12 +78,13 @@ def _ref_one(job):
     return r1.returncode, r2.returncode, time.perf_counter() - t0
 
 
-def reference_sample(files, flags, cores, keep_outputs=False):
+def reference_sample(files, flags, cores, keep_outputs=False, binary=None):
     """One reference process per file, `cores` at a time.  -> (GB/s, seconds, outputs|None)"""
     import pyoracle
     from concurrent.futures import ThreadPoolExecutor
-    if not os.path.exists(pyoracle.REF_BIN):
-        raise FileNotFoundError(pyoracle.REF_BIN)
+    binary = binary or pyoracle.REF_BIN
+    if not os.path.exists(binary):
+        raise FileNotFoundError(binary)
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
     tmp = tempfile.mkdtemp(prefix="hcref_", dir=base)
     try:
@@ -94,7 +95,7 @@ def reference_sample(files, flags, cores, keep_outputs=False):
             paths.append(p)
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=cores) as ex:
-            res = list(ex.map(_ref_one, [(pyoracle.REF_BIN, flags, p) for p in paths]))
+            res = list(ex.map(_ref_one, [(binary, flags, p) for p in paths]))
         wall = time.perf_counter() - t0
         assert all(a == 0 and b == 0 for a, b, _ in res), "reference binary failed"
         outs = None
@@ -397,6 +398,19 @@ def run_ours(args):
         if name in alg and ms > 0:
             a = alg[name] / (ms * 1e-3) / 1e9
             stages.append({"kernel": name, "ms": ms, "algorithmic_bytes": alg[name], "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak})
+    ncu_fgk = None
+    npath = os.path.join(ROOT, "profiles", "r01_ncu_fgk_final_metrics.json")
+    if os.path.exists(npath):
+        try:
+            nm = json.load(open(npath))
+            ncu_fgk = {"source": "profiles/r01_ncu_fgk_final_metrics.json (ncu --set full of this workload, not measured in this run)"}
+            for kname, met in nm.items():
+                ncu_fgk[kname.split(" ")[0]] = {
+                    "issue_active_pct": float(met["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+                    "warps_active_pct": float(met["sm__warps_active.avg.pct_of_peak_sustained_active"][0]),
+                    "warp_inst_executed": float(met["smsp__inst_executed.sum"][0])}
+        except (KeyError, ValueError, TypeError):
+            ncu_fgk = None
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and nf == 4096 and use_adapt:       # per-launch DRAM bytes from the committed ncu capture
@@ -415,7 +429,10 @@ def run_ours(args):
     for nm, d in (("fgk_encode", st_cmp), ("fgk_decode", st_dec)):
         if nm in d and d[nm] > 0:
             fgk[nm] = {"ms": d[nm], "symbols": m_sym, "streams": nf, "symbols_per_s": m_sym / (d[nm] * 1e-3),
+                       "streams_per_s": nf / (d[nm] * 1e-3),
                        "ns_per_symbol_longest_stream": d[nm] * 1e6 / float(max(int.from_bytes(bytes(h), "little") for h in hdr))}
+    if ncu_fgk:
+        fgk["ncu"] = ncu_fgk
 
     # ---- CPU baseline (bounded sample, rank 0, N == 1 only) -----------------------------------------
     cpu = None
@@ -432,6 +449,14 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "%d of the %d files (%d per class), reference binary -O2, -c then -d, one process per file, %d at a time, %.1f s wall; "
                              "GPU outputs byte-identical on the sample" % (n, nf, n // 4, cores, wall)}
+            try:   # the reference Makefile's own flags (-O0), same sample (both builds reported)
+                import pyoracle
+                v0, wall0, _ = reference_sample(files, ["-m"] + (["-a", "-w", str(N_SIDE)] if use_adapt else []), cores,
+                                                binary=pyoracle.REF_BIN_O0)
+                cpu["value_O0"] = v0
+                cpu["sample"] += "; value_O0 = the Makefile's -O0 build on the same sample, %.1f s wall" % wall0
+            except FileNotFoundError:
+                pass
         except FileNotFoundError:
             import pyoracle
             ora = pyoracle.Oracle()
