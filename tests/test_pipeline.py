@@ -251,3 +251,30 @@ def test_many_files_cross_group_pipeline(codec, oracle, monkeypatch):
     assert not st2.any()
     for i, b in zip(good, back):
         assert np.array_equal(b, files[i]), i
+
+
+@pytest.mark.gpu
+def test_mixed_entropy_stress_all_modes(oracle):
+    """Mini C5: random / smooth / const thirds plus walk, long-run and Fibonacci-skewed
+    streams, random shapes up to 300 x 300 (ragged edge blocks, every block-size path of the adaptive
+    coder), all four flag combinations, each output compared with the oracle and decoded back."""
+    cd = hc_b200.Codec(0)
+    rng = np.random.default_rng(31337)
+    kinds = ("random", "smooth", "const", "walk", "longrun", "fib")
+    files, widths = [], []
+    for i in range(180):
+        w = int(rng.integers(8, 300))
+        h = int(rng.integers(8, 300))
+        files.append(synth.image(kinds[i % 6], w, 5000 + i, h).reshape(-1))
+        widths.append(w)
+    for diff in (False, True):
+        for adapt in (False, True):
+            outs, st = cd.compress(files, diff=diff, adapt=adapt, width=widths)
+            assert not st.any()
+            for i, (f, w, o) in enumerate(zip(files, widths, outs)):
+                rc, exp = oracle.compress(f, diff=diff, adapt=adapt, width=w)
+                assert rc == 0 and np.array_equal(o, exp), (i, diff, adapt, w, f.size // w)
+            back, st2 = cd.decompress(outs)
+            assert not st2.any()
+            for i, (f, b) in enumerate(zip(files, back)):
+                assert np.array_equal(b, f), (i, diff, adapt)

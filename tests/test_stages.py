@@ -387,3 +387,58 @@ def test_rle_encode_long_runs(be, oracle):
     for i, (f, g) in enumerate(zip(files, dst.files(lens))):
         exp = oracle.rle_encode(f)
         assert int(lens[i]) == exp.size and np.array_equal(g, exp), (i, f.size)
+
+
+def _fgk_stress_inputs(be):
+    """Many streams with different symbol statistics: uniform, geometric (deep trees, leaves below the
+    path table), few symbols (internal nodes near the root swap often), sorted ramps, bursts."""
+    rng = np.random.default_rng(4242)
+    ns, nmax = (28, 2500) if be.name == "emu" else (224, 120000)
+    files = []
+    for i in range(ns):
+        n = int(rng.integers(1, nmax))
+        kind = i % 7
+        if kind == 0:
+            f = rng.integers(0, 256, n)
+        elif kind == 1:
+            f = np.minimum(rng.geometric(0.5 ** (1 + i % 3), n) - 1, 255)
+        elif kind == 2:
+            f = rng.integers(0, 2 + i % 5, n) * 37
+        elif kind == 3:
+            f = np.sort(rng.integers(0, 256, n))
+        elif kind == 4:
+            f = np.repeat(rng.integers(0, 256, n // 7 + 1), 7)[:n]
+        elif kind == 5:
+            f = (np.arange(n) // (1 + i)) & 255
+        else:
+            p = rng.dirichlet(np.full(64, 0.08))
+            f = rng.choice(64, n, p=p) * 3
+        files.append(np.asarray(f, np.uint8))
+    return files
+
+
+def test_fgk_stress_roundtrip(be, oracle):
+    files = _fgk_stress_inputs(be)
+    src = Batch(be, [f.size for f in files], files)
+    enc = Batch(be, [be.L.hc_fgk_bound(f.size) for f in files], fill=0xEE)
+    flags = be.upload(np.zeros(src.nf, np.uint8))
+    st = be.upload(np.zeros(src.nf, np.int32))
+    rc0(be.L.hc_fgk_encode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, flags.ptr, enc.data.ptr, enc.d_off.ptr,
+                                 enc.d_cap.ptr, enc.d_len.ptr, st.ptr, src.nf, be.stream))
+    assert not be.download(st, src.nf * 4, np.int32).any()
+    lens = enc.lens()
+    outs = enc.files(lens)
+    for i, (f, g) in enumerate(zip(files, outs)):
+        bits, _ = oracle.fgk_encode(f)
+        exp = np.concatenate([np.frombuffer(int(f.size).to_bytes(8, "little") + b"\0", np.uint8), bits])
+        assert int(lens[i]) == exp.size and np.array_equal(g, exp), (i, f.size)
+    # decode what was just produced
+    src2 = Batch(be, [o.size for o in outs], outs)
+    dst = Batch(be, [f.size for f in files], fill=0xEE)
+    fl = be.upload(np.zeros(src.nf, np.uint8))
+    st2 = be.upload(np.zeros(src.nf, np.int32))
+    rc0(be.L.hc_fgk_decode_batch(src2.data.ptr, src2.d_off.ptr, src2.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                 dst.d_len.ptr, fl.ptr, st2.ptr, src.nf, be.stream))
+    assert not be.download(st2, src.nf * 4, np.int32).any()
+    for i, (f, g) in enumerate(zip(files, dst.files(dst.lens()))):
+        assert np.array_equal(g, f), (i, f.size)
