@@ -4,10 +4,12 @@
 // header src/headers.cpp:107-125 and bit packing src/main.cpp:78-84.
 //
 // The tree update is serial inside one stream, so the parallelism is the batch: ONE WARP PER
-// FILE with the tree in shared memory (6.7 KB per stream).  All 32 lanes execute the same control
-// flow and only READ the tree; lane 0 is the only writer.  The kernel is instruction-issue bound
-// (about 7 resident streams per warp scheduler at 4096 files), so the layout is chosen to make
-// the per-level work of the leaf->root walk as few instructions as possible:
+// FILE with the tree in shared memory (9.9 KB per stream, 20 streams per SM).  All 32 lanes execute
+// the same control flow; lane 0 is the only writer of links.  The kernel is bound by the chain of
+// dependent instructions of one warp (a lone high-entropy stream is only 15-20 % faster than the
+// whole batch), so everything is arranged to shorten that chain: a PATH TABLE (below, at FgkTree)
+// lets the 32 lanes look at all levels of a root->leaf path at once, and the layout makes the
+// per-level work of the remaining sequential walks as few instructions as possible:
 //
 //   slot = node number 0..512: siblings adjacent, even slot = left child = bit 0,
 //   weights non-decreasing in slot order, so the block leader of s is the last slot l >= s with
@@ -16,11 +18,12 @@
 //   down[s] = internal: shared address of down[left child]; leaf: (symbol << 1) | 1
 //   The code bit of slot s is bit 3 of the address of up[s] (8-byte entries, 16-byte aligned base).
 //
-//   per level: LDS.64 up[s], LDS.32 up[s+1].w -> if the weights differ (common case) there is no
-//   leader to find: lane 0 stores w+1 and the walk follows the parent address.  Only when they are
-//   equal the warp probes 32 slots per ballot for the leader and, if needed, swaps the two subtrees.
-//   Encoding collects the code bits on the same walk (shifted in from the top, a marker bit
-//   tracks the length) until the first swap, after which the old path is finished separately.
+//   sequential walk, per level: LDS.64 up[s], LDS.32 up[s+1].w -> if the weights differ (common
+//   case) there is no leader to find: lane 0 stores w+1 and the walk follows the parent address.
+//   Only when they are equal the warp probes 32 slots per ballot for the leader and, if needed,
+//   swaps the two subtrees.  Used for nodes deeper than the path table; there encoding collects the
+//   code bits on the same walk (shifted in from the top, a marker bit tracks the length) until
+//   the first swap, after which the old path is finished alongside the rest of the update.
 //
 // Bits are packed MSB-first into 32-bit words; each lane keeps one word and the warp flushes
 // 128 bytes at a time (coalesced).  The 9-byte container header goes through the same writer.

@@ -7,18 +7,24 @@
 // ENCODE.  Per element: k = index inside its maximal run (runs are taken over elements
 // 0..n-2, the last element is always its own literal), q = k mod 258.  The element emits
 //      [q < 3] its byte, [q == 257] the byte 255, [last of run && 2 <= q < 257] the count q-2.
-// k comes from a block-wide max-scan of run-start positions, the output position from a
-// block-wide exclusive add-scan of the per-element byte counts (0, 1 or 2).  Output bytes are
-// staged in shared memory with the same 16-byte phase as the global destination and copied
-// out with 128-bit stores.
+// A thread owns 16-byte vectors: equality bits by byte-SIMD compares, the two emission masks by
+// bit logic on them (rle_vec_masks; k of a vector's first element comes from a block-wide max-scan
+// of run-start positions), the output position from a block-wide exclusive add-scan of the
+// per-vector byte counts.  Output assembly is per 4-byte word: a count replaces the byte of its
+// (non-literal) element, then one PRMT with a selector from a 256-entry table compacts the word.
+// Bytes are staged in shared memory with the same 16-byte phase as the global destination and
+// copied out with 128-bit stores.
 //
 // DECODE.  Whether an input byte is a literal or a count depends on the decoder state
 // c in {0,1,2,3}, whose transition only needs c and e[i] = (in[i] == in[i-1]).  Each position is
-// therefore a 4->4 map (8 bits); a block-wide scan under function composition classifies
-// every byte.  A second add-scan of the token lengths (literal 1, count = byte value) places
-// the output.  Expansion is done per 16 KiB output window: every token drops its value and a
-// head flag at its first output position, then each thread propagates the last head value
-// over 64 consecutive output bytes (a max-scan finds the head that reaches into its range).
+// therefore a 4->4 map, kept one byte per state so that composing two maps is one PRMT; the map
+// of 8 positions comes from a table indexed by their equality bits, and a block-wide scan under
+// composition gives every vector its entry state.  A second table turns (state, 8 equality bits)
+// into "which of these bytes are counts"; a block-wide add-scan of the vector lengths (literals +
+// the sum of the count bytes) places the output.  Expansion is done per 16 KiB output window:
+// every token drops its value and a head flag at its first output position, then each thread
+// fills 64 consecutive output bytes from the last head value (a max-scan finds the head that
+// reaches into its range), 16 bytes at a time with shortcuts for all-literal and in-run chunks.
 #pragma once
 #include "runsum.cuh"
 #include "scan.cuh"
@@ -251,7 +257,6 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
     const u32 dphase = (u32)((uintptr_t)dst & 15u);
     const u32 *lut = rle_enc_lut();
     {
-        {
         u64 out_pos = 0;      // bytes emitted by all previous tiles
         u32 carry_run = 0;    // length of the run that ends at the last element of the previous tile
 
@@ -353,7 +358,6 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
             syncthreads();
         }
         return out_pos;
-        }
     }
 }
 
