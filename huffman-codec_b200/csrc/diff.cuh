@@ -12,43 +12,52 @@
 namespace hcd {
 
 // ---------------------------------------------------------------- apply
+// A CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of a file and keeps the loads of the
+// next tile in flight while the current one is computed and stored.
 HC_KERNEL HC_LAUNCH_BOUNDS(256, 4)
 diff_apply_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, u8 *HC_RESTRICT out,
                   const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT len, u32 nf)
 {
     const u32 tid = threadIdx.x, lane = tid & 31;
+    const u64 step = (u64)gridDim.x * TILE_BYTES;
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
         const u64 n = len[f];
-        const u64 tile0 = (u64)blockIdx.x * TILE_BYTES;
-        if (tile0 >= n) continue;
         const u8 *src = in + in_off[f];
         u8 *dst = out + out_off[f];
-        uint4 v[UN];
-        u32 halo[UN];
+        uint4 cur[UN], nxt[UN];
+        u32 hcur[UN], hnxt[UN];                          // lane 0: the byte before its vector
+        u64 t0 = (u64)blockIdx.x * TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < UN; j++) {
-            u64 p = tile0 + (u64)j * SUB_BYTES + tid * 16;
-            v[j] = make_uint4_zero();
-            halo[j] = 0;
-            if (p < n) {
-                v[j] = ldg16(src + p);
-                if (lane == 0 && p > 0) halo[j] = ldg8(src + p - 1);
-            }
+            const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
+            cur[j] = p < n ? ldg16(src + p) : make_uint4_zero();
+            hcur[j] = (lane == 0 && p > 0 && p < n) ? ldg8(src + p - 1) : 0u;
         }
+        for (; t0 < n; t0 += step) {
 #pragma unroll
-        for (int j = 0; j < UN; j++) {
-            u64 p = tile0 + (u64)j * SUB_BYTES + tid * 16;
-            u32 up = shfl_up(v[j].w >> 24, 1);      // last byte of the previous lane's vector
-            u32 prev = lane == 0 ? halo[j] : up;
-            uint4 r;
-            r.x = vsub4(v[j].x, (v[j].x << 8) | prev);
-            r.y = vsub4(v[j].y, (v[j].y << 8) | (v[j].x >> 24));
-            r.z = vsub4(v[j].z, (v[j].z << 8) | (v[j].y >> 24));
-            r.w = vsub4(v[j].w, (v[j].w << 8) | (v[j].z >> 24));
-            if (p < n) {
-                if (p + 16 > n) r = mask_tail(r, (u32)(n - p));   // zero the padding bytes
-                stg16(dst + p, r);
+            for (int j = 0; j < UN; j++) {
+                const u64 p = t0 + step + (u64)j * SUB_BYTES + tid * 16;
+                nxt[j] = p < n ? ldg16(src + p) : make_uint4_zero();
+                hnxt[j] = (lane == 0 && p < n) ? ldg8(src + p - 1) : 0u;
             }
+#pragma unroll
+            for (int j = 0; j < UN; j++) {
+                const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
+                const uint4 v = cur[j];
+                const u32 up = shfl_up(v.w >> 24, 1);   // last byte of the previous lane's vector
+                const u32 prev = lane == 0 ? hcur[j] : up;
+                uint4 r;
+                r.x = vsub4(v.x, (v.x << 8) | prev);
+                r.y = vsub4(v.y, (v.y << 8) | (v.x >> 24));
+                r.z = vsub4(v.z, (v.z << 8) | (v.y >> 24));
+                r.w = vsub4(v.w, (v.w << 8) | (v.z >> 24));
+                if (p < n) {
+                    if (p + 16 > n) r = mask_tail(r, (u32)(n - p));   // zero the padding bytes
+                    stg16(dst + p, r);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UN; j++) { cur[j] = nxt[j]; hcur[j] = hnxt[j]; }
         }
     }
 }

@@ -225,7 +225,10 @@ extern "C" int hc_diff_apply_batch(const uint8_t *in, const uint64_t *in_off, ui
 {
     if (nf == 0) return 0;
     u64 tiles = (max_len + TILE_BYTES - 1) / TILE_BYTES;
-    HC_LAUNCH(diff_apply_kernel, grid2(tiles, nf), dim3(TPB), 0, stream, in, in_off, out, out_off, len, nf);
+    // enough CTAs for two full waves (148 SMs x 8 resident), each streaming several tiles of its file
+    u64 gx = (2368 + nf - 1) / nf;
+    if (gx > tiles) gx = tiles;
+    HC_LAUNCH(diff_apply_kernel, grid2(gx, nf), dim3(TPB), 0, stream, in, in_off, out, out_off, len, nf);
     HC_CHECK_LAUNCH();
     return 0;
 }
