@@ -233,14 +233,27 @@ extern "C" int hc_diff_apply_batch(const uint8_t *in, const uint64_t *in_off, ui
     return 0;
 }
 
-extern "C" int hc_diff_revert_batch(const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
-                                    const uint64_t *len, uint32_t nf, uint64_t max_len, hc_stream_t stream)
+// scratch of the segmented scan: one u32 per (file, segment); 0 when the batch needs no segments
+static inline u64 diff_revert_ws_bytes(u32 nf, u64 max_len)
+{
+    const SegPlan p = plan_segments(nf, max_len);
+    return p.nseg > 1 ? (u64)nf * p.nseg * sizeof(u32) : 0;
+}
+
+// ws: caller-owned scratch of diff_revert_ws_bytes() bytes, or NULL (stream-ordered allocation)
+static int diff_revert_launch(const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
+                              const uint64_t *len, uint32_t nf, uint64_t max_len, void *ws, hc_stream_t stream)
 {
     if (nf == 0) return 0;
     SegPlan p = plan_segments(nf, max_len);
     u32 *segsum = nullptr;
+    bool own = false;
     if (p.nseg > 1) {
-        HC_CUDA(cudaMallocAsync((void **)&segsum, (size_t)nf * p.nseg * sizeof(u32), (cudaStream_t)stream));
+        segsum = (u32 *)ws;
+        if (!segsum) {
+            HC_CUDA(cudaMallocAsync((void **)&segsum, (size_t)nf * p.nseg * sizeof(u32), (cudaStream_t)stream));
+            own = true;
+        }
         HC_LAUNCH(diff_segsum_kernel, grid2(p.nseg, nf), dim3(TPB), 0, stream, in, in_off, len, nf, p.nseg,
                   p.seg_bytes, segsum);
         HC_CHECK_LAUNCH();
@@ -248,8 +261,14 @@ extern "C" int hc_diff_revert_batch(const uint8_t *in, const uint64_t *in_off, u
     HC_LAUNCH(diff_revert_kernel, grid2(p.nseg, nf), dim3(TPB), 0, stream, in, in_off, out, out_off, len, nf,
               p.nseg, p.seg_bytes, (const u32 *)segsum);
     HC_CHECK_LAUNCH();
-    if (segsum) HC_CUDA(cudaFreeAsync(segsum, (cudaStream_t)stream));
+    if (own) HC_CUDA(cudaFreeAsync(segsum, (cudaStream_t)stream));
     return 0;
+}
+
+extern "C" int hc_diff_revert_batch(const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
+                                    const uint64_t *len, uint32_t nf, uint64_t max_len, hc_stream_t stream)
+{
+    return diff_revert_launch(in, in_off, out, out_off, len, nf, max_len, nullptr, stream);
 }
 
 static inline unsigned file_grid(uint32_t nf) { return nf > 0x7fffffffu ? 0x7fffffffu : (nf ? nf : 1u); }
@@ -549,6 +568,7 @@ struct hc_codec {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevBuf in, a, b, out, tab, ws, ord;  // raw input, stage buffers, strided output, tables, scratch, FGK start order
+    DevBuf jt;                           // offset / length / status tables of a host-level call (group pipelines)
     HostBuf htab;
     bool timing = false;
     cudaEvent_t ev[HC_MAX_STAGES + 1];
@@ -600,7 +620,7 @@ extern "C" void hc_codec_destroy(hc_codec *c)
     c->kids.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release(); c->ord.release();
+    c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release(); c->ord.release(); c->jt.release();
     c->htab.release();
     if (c->ev_ready) for (int i = 0; i <= HC_MAX_STAGES; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
@@ -757,7 +777,9 @@ static int dec_expand(hc_codec *c, uint32_t nf, uint64_t max_sym_len, uint64_t m
               (const u64 *)t.u64_at(T_N_AD), (const i32 *)t.i32_at(T_ST2), d_out_len, t.u64_at(T_LEN_DIFF), d_status, nf);
     HC_CHECK_LAUNCH();
     if ((kinds & HC_KIND_DIFF) && d_out) {
-        HC_TRY(hc_diff_revert_batch(d_out, d_out_off, d_out, d_out_off, t.u64_at(T_LEN_DIFF), nf, max_out_len, s));
+        // the adaptive / RLE expansion is done with c->ws by now (same stream): reuse it for the segment sums
+        HC_TRY(c->ws.ensure((size_t)diff_revert_ws_bytes(nf, max_out_len) + 16));
+        HC_TRY(diff_revert_launch(d_out, d_out_off, d_out, d_out_off, t.u64_at(T_LEN_DIFF), nf, max_out_len, c->ws.p, s));
         stage_mark(c, "diff_revert");
     }
     return 0;
@@ -811,12 +833,6 @@ static int upload_files(hc_codec *c, DevBuf &dst, const uint8_t *base, const uin
     return 0;
 }
 
-struct AsyncFree {   // stream-ordered scratch released on every exit path
-    void *p = nullptr;
-    cudaStream_t s = nullptr;
-    ~AsyncFree() { if (p) cudaFreeAsync(p, s); }
-};
-
 // ---- group pipelines -----------------------------------------------------------------------------
 // The host-level calls split large batches into up to HC_MAX_GROUPS contiguous groups of files, each with
 // its own stream and buffers (a child codec).  Host<->device copies of one group overlap the kernels
@@ -855,7 +871,6 @@ static void group_range(u32 nf, u32 g, u32 ng, u32 *lo, u32 *hi)
 
 struct GroupJob {
     u32 lo = 0, hi = 0;
-    AsyncFree dev;
     u64 *d = nullptr;           // device tables
     u64 max_a = 0, max_b = 0;   // per-call maxima (meaning depends on the direction)
     int kinds = 0;
@@ -901,9 +916,10 @@ extern "C" int hc_compress_batch(hc_codec *c,
         }
         j.max_a = max_len;
         HC_TRY(k->out.ensure((size_t)pos + 512));
-        j.dev.s = s;
-        HC_CUDA(cudaMallocAsync(&j.dev.p, N * 8 * 9, s));       // 7 tables + out_len + status
-        j.d = (u64 *)j.dev.p;
+        // codec-owned (not cudaMallocAsync: with the default pool's release threshold every call pays a
+        // fresh mapping, measured as stalls of up to 200 ms)
+        HC_TRY(k->jt.ensure(N * 8 * 9));                        // 7 tables + out_len + status
+        j.d = (u64 *)k->jt.p;
         u64 *d = j.d;
         HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 5, cudaMemcpyHostToDevice, s));
         HC_TRY(hc_compress_device(k, (const u8 *)k->in.p, d, d + N, d + 2 * N, n, max_len, use_diff, use_adapt,
@@ -994,9 +1010,8 @@ extern "C" int hc_decompress_batch(hc_codec *c,
         HC_TRY(k->htab.ensure(N * 8 * 6));
         u64 *h = (u64 *)k->htab.p;
         for (u32 i = 0; i < n; i++) { h[i] = d_off[i]; h[N + i] = in_len[j.lo + i]; }
-        j.dev.s = s;
-        HC_CUDA(cudaMallocAsync(&j.dev.p, N * 8 * 6, s));
-        j.d = (u64 *)j.dev.p;
+        HC_TRY(k->jt.ensure(N * 8 * 6));
+        j.d = (u64 *)k->jt.p;
         u64 *d = j.d;
         HC_CUDA(cudaMemcpyAsync(d, h, N * 8 * 2, cudaMemcpyHostToDevice, s));
         stage_begin(k);
