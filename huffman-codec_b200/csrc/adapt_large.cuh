@@ -115,7 +115,9 @@ adapt_gather_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_of
             const u32 strip = (u32)(it % spb1);
             const BlockGeom g = ad_geom(w, h, b, blk);
             if (strip * ADL_T >= g.bh) continue;
-            adl_move_strip((u8 *)(in + in_off[f]), w, g, tab[blk] >> 31, tmp + (u64)f * tstride + adl_slot(w, h, b, blk),
+            const bool hor = tab[blk] >> 31;
+            if (hor && g.bw == w) continue;                    // full-width horizontal block: already a stream
+            adl_move_strip((u8 *)(in + in_off[f]), w, g, hor, tmp + (u64)f * tstride + adl_slot(w, h, b, blk),
                            strip, true, tile);
         }
     }
@@ -124,7 +126,8 @@ adapt_gather_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_of
 HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
 adapt_emit_large_kernel(const u8 *HC_RESTRICT tmp, u64 tstride, const u64 *HC_RESTRICT width, const u64 *HC_RESTRICT height,
                         u32 nf, const u32 *HC_RESTRICT blk_off, u64 off_stride, const u64 *HC_RESTRICT chosen_b,
-                        u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status)
+                        u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status,
+                        const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u32 *HC_RESTRICT cost, u64 cost_stride)
 {
     rle_enc_init();
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
@@ -134,9 +137,16 @@ adapt_emit_large_kernel(const u8 *HC_RESTRICT tmp, u64 tstride, const u64 *HC_RE
         const u32 *bo = blk_off + (u64)f * off_stride;
         const u64 nb = ad_nblocks(w, h, b);
         u8 *data = out + out_off[f] + 24 + (nb + 7) / 8;
+        int k = 0;
+        while ((8ull << k) < b) k++;
+        const u32 *tab = cost + (u64)f * cost_stride + ad_kbase(w, h, k);
         for (u64 blk = blockIdx.x; blk < nb; blk += gridDim.x) {
             const BlockGeom g = ad_geom(w, h, b, blk);
-            rle_encode_stream(tmp + (u64)f * tstride + adl_slot(w, h, b, blk), (u64)g.bw * g.bh, data + bo[blk]);
+            // a full-width horizontal block is contiguous in the matrix (16-byte aligned: the file slot is
+            // 256-byte aligned and the block starts b rows down, b % 16 == 0): encode it in place
+            const u8 *src = ((tab[blk] >> 31) && g.bw == w) ? in + in_off[f] + g.base
+                                                            : tmp + (u64)f * tstride + adl_slot(w, h, b, blk);
+            rle_encode_stream(src, (u64)g.bw * g.bh, data + bo[blk]);
         }
     }
 }
@@ -144,7 +154,7 @@ adapt_emit_large_kernel(const u8 *HC_RESTRICT tmp, u64 tstride, const u64 *HC_RE
 HC_KERNEL HC_LAUNCH_BOUNDS(256, 2)
 adapt_expand_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                           const u32 *HC_RESTRICT blk_start, u64 blk_stride, const i32 *HC_RESTRICT status, u32 nf,
-                          u8 *HC_RESTRICT tmp, u64 tstride)
+                          u8 *HC_RESTRICT tmp, u64 tstride, u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off)
 {
     rle_dec_init();
     for (u32 f = blockIdx.y; f < nf; f += gridDim.y) {
@@ -156,9 +166,11 @@ adapt_expand_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_of
         for (u64 blk = blockIdx.x; blk < hd.nb; blk += gridDim.x) {
             const BlockGeom g = ad_geom(hd.w, hd.h, hd.b, blk);
             const u32 t0 = tab[blk], t1 = tab[blk + 1];
+            const bool hor = (src[24 + (blk >> 3)] >> (7 - (blk & 7))) & 1u;
+            // a full-width horizontal block is decoded straight into the matrix (see adapt_emit_large_kernel)
+            u8 *dst = (hor && g.bw == hd.w) ? out + out_off[f] + g.base : tmp + (u64)f * tstride + adl_slot(hd.w, hd.h, hd.b, blk);
             // adapt_index_kernel has validated the stream: these tokens decode to exactly bw*bh bytes
-            rle_decode_stream(src + t0, (u64)(t1 - t0), tmp + (u64)f * tstride + adl_slot(hd.w, hd.h, hd.b, blk),
-                              (u64)g.bw * g.bh);
+            rle_decode_stream(src + t0, (u64)(t1 - t0), dst, (u64)g.bw * g.bh);
         }
     }
 }
@@ -181,6 +193,7 @@ adapt_scatter_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_o
             const BlockGeom g = ad_geom(hd.w, hd.h, hd.b, blk);
             if (strip * ADL_T >= g.bh) continue;
             const bool hor = (src[24 + (blk >> 3)] >> (7 - (blk & 7))) & 1u;
+            if (hor && g.bw == hd.w) continue;                 // decoded in place by adapt_expand_large_kernel
             adl_move_strip(out + out_off[f], hd.w, g, hor, (u8 *)tmp + (u64)f * tstride + adl_slot(hd.w, hd.h, hd.b, blk),
                            strip, false, tile);
         }

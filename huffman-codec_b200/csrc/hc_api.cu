@@ -363,7 +363,7 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
         u64 gb = max_len / (ADL_MINB * ADL_MINB) + 1;
         if (gb > 16) gb = 16;
         HC_LAUNCH(adapt_emit_large_kernel, grid2(gb, nf), dim3(TPB), 0, stream, (const u8 *)ltmp, tstride, width, height, nf,
-                  (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status);
+                  (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status, in, in_off, (const u32 *)cost, cs);
         HC_CHECK_LAUNCH();
     }
     // files whose winning block size is 8/16/32: one thread per block over shared-memory staged rows
@@ -428,7 +428,7 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
         u64 gb = max_out_len / (ADL_MINB * ADL_MINB) + 1;
         if (gb > 16) gb = 16;
         HC_LAUNCH(adapt_expand_large_kernel, grid2(gb, nf), dim3(TPB), 0, stream, in, in_off, in_len, (const u32 *)ws, bs,
-                  (const i32 *)status, nf, ltmp, tstride);
+                  (const i32 *)status, nf, ltmp, tstride, out, out_off);
         HC_CHECK_LAUNCH();
         u64 gx = max_out_len / (ADL_T * ADL_T) + 1;
         if (gx > 64) gx = 64;
