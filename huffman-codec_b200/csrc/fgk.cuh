@@ -32,10 +32,17 @@
 
 namespace hcd {
 
-#ifndef HC_FGK_WARPS
-#define HC_FGK_WARPS 4
+#ifndef HC_FGK_ENC_WARPS
+#define HC_FGK_ENC_WARPS 1
 #endif
-constexpr int FGK_WARPS = HC_FGK_WARPS;  // streams per CTA (4 = one per SM sub-partition; measured best on B200)
+#ifndef HC_FGK_DEC_WARPS
+#define HC_FGK_DEC_WARPS 4
+#endif
+// streams per CTA.  Measured on C3 (final kernels): encoder 1 / 2 / 3 / 4 -> 152 / 178-186 / 183 / 174 ms, decoder
+// 1 / 2 / 4 -> 205 / 201 / 198 ms.  One-warp CTAs give their 9.9 KB back as soon as their stream ends.
+constexpr int FGK_ENC_WARPS = HC_FGK_ENC_WARPS;
+constexpr int FGK_DEC_WARPS = HC_FGK_DEC_WARPS;
+constexpr int FGK_WARPS = FGK_ENC_WARPS > FGK_DEC_WARPS ? FGK_ENC_WARPS : FGK_DEC_WARPS;
 constexpr u32 FGK_ROOT = 512;
 constexpr u32 FGK_NSLOT = 514;           // slots 0..512 + one sentinel (weight 0xffffffff)
 constexpr u32 FGK_LEAF_NYT = (256u << 1) | 1u;
@@ -569,16 +576,16 @@ HC_DEV u64 bw_finish(BitWriter &b, u32 lane)
     return total;
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(FGK_WARPS * 32, 1)
+HC_KERNEL HC_LAUNCH_BOUNDS(FGK_ENC_WARPS * 32, 1)
 fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, const u64 *HC_RESTRICT sym_len,
                   const u8 *HC_RESTRICT flags, u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off,
                   const u64 *HC_RESTRICT out_cap, u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf,
                   const u32 *HC_RESTRICT order)
 {
-    HC_SHARED FgkTree trees[FGK_WARPS];
+    HC_SHARED FgkTree trees[FGK_ENC_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 fi = blockIdx.x * FGK_WARPS + wid;
+    const u32 fi = blockIdx.x * FGK_ENC_WARPS + wid;
     if (fi >= nf) return;
     const u32 f = order ? order[fi] : fi;               // longest streams first (fgk_order_kernel)
     FgkCtx c;
@@ -704,16 +711,16 @@ HC_DEV u32 br_get(BitReader &r, u32 d, u32 lane)   // 1..32 bits; caller checks 
     return v;
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(FGK_WARPS * 32, 1)
+HC_KERNEL HC_LAUNCH_BOUNDS(FGK_DEC_WARPS * 32, 1)
 fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, const u64 *HC_RESTRICT sym_cap,
                   u64 *HC_RESTRICT sym_len, u8 *HC_RESTRICT flags, i32 *HC_RESTRICT status, u32 nf,
                   const u32 *HC_RESTRICT order)
 {
-    HC_SHARED FgkTree trees[FGK_WARPS];
+    HC_SHARED FgkTree trees[FGK_DEC_WARPS];
     HC_SMEM_ARENA(trees);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 fi = blockIdx.x * FGK_WARPS + wid;
+    const u32 fi = blockIdx.x * FGK_DEC_WARPS + wid;
     if (fi >= nf) return;
     const u32 f = order ? order[fi] : fi;               // longest streams first (fgk_order_kernel)
     FgkCtx c;

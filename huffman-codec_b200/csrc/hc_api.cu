@@ -467,7 +467,7 @@ static int fgk_encode_launch(const uint8_t *sym, const uint64_t *sym_off, const 
         HC_LAUNCH(fgk_order_kernel, dim3(1), dim3(1024), 0, stream, sym_len, nf, order_ws);
         HC_CHECK_LAUNCH();
     }
-    HC_LAUNCH(fgk_encode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, sym,
+    HC_LAUNCH(fgk_encode_kernel, dim3((nf + FGK_ENC_WARPS - 1) / FGK_ENC_WARPS), dim3(FGK_ENC_WARPS * 32), 0, stream, sym,
               sym_off, sym_len, flags, out, out_off, out_cap, out_len, status, nf, (const u32 *)order_ws);
     HC_CHECK_LAUNCH();
     return 0;
@@ -492,7 +492,7 @@ static int fgk_decode_launch(const uint8_t *in, const uint64_t *in_off, const ui
         HC_LAUNCH(fgk_order_kernel, dim3(1), dim3(1024), 0, stream, in_len, nf, order_ws);   // compressed bytes ~ work
         HC_CHECK_LAUNCH();
     }
-    HC_LAUNCH(fgk_decode_kernel, dim3((nf + FGK_WARPS - 1) / FGK_WARPS), dim3(FGK_WARPS * 32), 0, stream, in,
+    HC_LAUNCH(fgk_decode_kernel, dim3((nf + FGK_DEC_WARPS - 1) / FGK_DEC_WARPS), dim3(FGK_DEC_WARPS * 32), 0, stream, in,
               in_off, in_len, sym, sym_off, sym_cap, sym_len, flags, status, nf, (const u32 *)order_ws);
     HC_CHECK_LAUNCH();
     return 0;
