@@ -57,8 +57,8 @@ constexpr u32 FGK_NOPATH = 0xffffu;
 // knows every node on the way; encoding takes the code of a leaf straight from pfx; and the
 // update's "does this level need a swap" test runs for all levels of the path in one ballot.
 // The table describes SLOTS, so the most frequent swap (two leaves exchange their symbols) leaves it
-// valid; it is rebuilt (warp-parallel, level by level) after a swap that moves an internal node and
-// after an NYT split.  Deeper levels fall back to the sequential walks.
+// valid; a swap that moves an internal node re-derives the entries below the two slots (warp-parallel,
+// level by level), an NYT split adds its two entries.  Deeper levels fall back to the sequential walks.
 struct HC_ALIGNED16 FgkTree {
     uint2 up[FGK_NSLOT];     // {weight, shared address of the parent's up entry}
     u32 down[FGK_NSLOT];     // see above
@@ -68,6 +68,8 @@ struct HC_ALIGNED16 FgkTree {
     u8 buf[128];             // staging of 128 symbols (one coalesced transfer)
     u8 pad[8];
 };
+
+static_assert(sizeof(FgkTree) * FGK_WARPS <= 48u * 1024u, "the trees of a CTA are static shared memory");
 
 struct FgkCtx {              // shared addresses, identical in every lane
     u32 up, down, slot_of, buf, root, sentinel, nyt;
