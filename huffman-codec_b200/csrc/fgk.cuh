@@ -74,6 +74,7 @@ static_assert(sizeof(FgkTree) * FGK_WARPS <= 48u * 1024u, "the trees of a CTA ar
 struct FgkCtx {              // shared addresses, identical in every lane
     u32 up, down, slot_of, buf, root, sentinel, nyt;
     u32 pt, pfx, lev;        // lev: number of populated levels of pt
+    u32 fl;                  // out-of-line helpers: bit 0 = the watched leaf moved
 };
 
 HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
@@ -88,6 +89,7 @@ HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
     c.pt = smem_addr(&t.pt[0]);
     c.pfx = smem_addr(&t.pfx[0]);
     c.lev = 0;
+    c.fl = 0;
     for (u32 i = lane; i < 128u; i += 32) sts32(c.slot_of + 4u * i, 0xffffffffu);
     for (u32 i = lane; i < (FGK_PT_N + 2u) / 2u; i += 32) sts32(c.pt + 4u * i, 0u);
     for (u32 i = lane; i < (FGK_NSLOT + 2u) / 2u; i += 32) sts32(c.pfx + 4u * i, 0xffffffffu);
@@ -327,6 +329,19 @@ HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, b
     syncwarp();
 }
 
+// Out-of-line forms of the sequential walks for the rare callers (nodes deeper than the path table,
+// the first occurrence of a symbol): one copy of the code instead of one per call site keeps the
+// kernels inside the instruction cache.  The context travels by value so that the caller's copy can
+// stay in registers; the full table rebuild is included.
+HC_DEV_NOINLINE FgkCtx fgk_update_plain_cold(FgkCtx c, u32 a, u32 lane, u32 count, u32 watch)
+{
+    bool moved = false, sc = false;
+    fgk_update_plain(c, a, lane, count, watch, moved, sc);
+    if (sc) fgk_rebuild(c, lane);
+    c.fl = moved ? 1u : 0u;
+    return c;
+}
+
 // FGK update of node a whose path is in the table (pf = its pfx entry): lane j takes the node at
 // depth j + 1, one ballot tells which levels need the leader search.  Levels below the deepest such
 // level are plain increments and done at once; that level is handled by fgk_leader_swap, after which
@@ -340,9 +355,8 @@ HC_DEV void fgk_update_fast(FgkCtx &c, u32 a, u32 pf, u32 lane, u32 count, u32 w
 {
     for (;;) {
         if (pf == FGK_NOPATH) {                           // deeper than the table: sequential walk
-            bool sc = false;
-            fgk_update_plain(c, a, lane, count, watch, moved, sc);
-            if (sc) fgk_rebuild(c, lane);
+            c = fgk_update_plain_cold(c, a, lane, count, watch);
+            if (c.fl & 1u) moved = true;
             return;
         }
         const u32 depth = pf >> 12, path = pf & 0xfffu;
@@ -630,9 +644,8 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
                 const u32 nsl = c.nyt, npf = nsl == c.root ? 0u : lds16(c.pfx + ((nsl - c.up) >> 2));
                 const u32 leaf = fgk_split(c, y, lane);
                 fgk_table_split(c, nsl, npf, lane);
-                bool sc = false;
-                fgk_update_plain(c, leaf, lane, count, yn, moved, sc);
-                if (sc) fgk_rebuild(c, lane);
+                c = fgk_update_plain_cold(c, leaf, lane, count, yn);
+                if (c.fl & 1u) moved = true;
                 if (yn == y) moved = true;
             } else {
                 const u32 pf = lds16(c.pfx + 2u * slot);
@@ -825,8 +838,7 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                 const u32 nsl = c.nyt, npf = nsl == c.root ? 0u : lds16(c.pfx + ((nsl - c.up) >> 2));
                 const u32 a = fgk_split(c, y, lane);
                 fgk_table_split(c, nsl, npf, lane);
-                fgk_update_plain(c, a, lane, count, 0x1ffu, moved, sc);  // ends with a warp barrier
-                if (sc) fgk_rebuild(c, lane);
+                c = fgk_update_plain_cold(c, a, lane, count, 0x1ffu);     // ends with a warp barrier
             } else {
                 fgk_update_fast(c, c.up + 8u * ex, lds16(c.pfx + 2u * ex), lane, count, 0x1ffu, moved);
             }
@@ -851,12 +863,10 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
                 } else {
                     const u32 k0 = 31u - (u32)clz(tm);                   // deepest level with a tie
                     sts32_if(valid && lane > k0, A, W + 1u);             // plain levels below it
-                    fgk_update_plain(c, shfl(A, (int)k0), lane, count, 0x1ffu, moved, sc);
-                    if (sc) fgk_rebuild(c, lane);
+                    c = fgk_update_plain_cold(c, shfl(A, (int)k0), lane, count, 0x1ffu);
                 }
             } else {
-                fgk_update_plain(c, fgk_up_of(c, d), lane, count, 0x1ffu, moved, sc);
-                if (sc) fgk_rebuild(c, lane);
+                c = fgk_update_plain_cold(c, fgk_up_of(c, d), lane, count, 0x1ffu);
             }
         }
         if ((i & 127u) == 127u) {
