@@ -496,8 +496,7 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
 
 // The trees of the resident CTAs no longer hold the whole batch at once, so streams are started in
 // order of decreasing length class (counting sort, 4 classes per octave): the long ones first, the
-// short ones fill the slots they free.  One CTA; the order inside a class is arbitrary (it only
-// affects scheduling, never the output).
+// short ones fill the slots they free.  One CTA; the order only affects scheduling, never the output.
 HC_KERNEL HC_LAUNCH_BOUNDS(1024, 1)
 fgk_order_kernel(const u64 *HC_RESTRICT len, u32 nf, u32 *HC_RESTRICT order)
 {
@@ -517,6 +516,20 @@ fgk_order_kernel(const u64 *HC_RESTRICT len, u32 nf, u32 *HC_RESTRICT order)
         for (int b = 255; b >= 0; b--) { const u32 h = hist[b]; hist[b] = acc; acc += h; }
     }
     syncthreads();
+    if (nf <= 65536u) {
+        // stable (file order inside a class, so the schedule is the same in every run): thread t places the
+        // files of class t
+        if (tid < 256u) {
+            u32 pos = hist[tid];
+            for (u32 f = 0; f < nf; f++) {
+                const u64 v = len[f];
+                u32 cl = 0;
+                if (v) { const u32 lg = 63u - (u32)clzll(v); cl = 4u * lg + (u32)((lg >= 2u ? v >> (lg - 2u) : v << (2u - lg)) & 3u); }
+                if ((cl > 255u ? 255u : cl) == tid) order[pos++] = f;
+            }
+        }
+        return;
+    }
     for (u32 f = tid; f < nf; f += blockDim.x) {
         const u64 v = len[f];
         u32 cl = 0;
