@@ -497,45 +497,39 @@ HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u3
 // The trees of the resident CTAs no longer hold the whole batch at once, so streams are started in
 // order of decreasing length class (counting sort, 4 classes per octave): the long ones first, the
 // short ones fill the slots they free.  One CTA; the order only affects scheduling, never the output.
+HC_DEV u32 fgk_len_class(u64 v)
+{
+    if (!v) return 0;
+    const u32 lg = 63u - (u32)clzll(v);
+    const u32 cl = 4u * lg + (u32)((lg >= 2u ? v >> (lg - 2u) : v << (2u - lg)) & 3u);
+    return cl > 255u ? 255u : cl;
+}
+
 HC_KERNEL HC_LAUNCH_BOUNDS(1024, 1)
 fgk_order_kernel(const u64 *HC_RESTRICT len, u32 nf, u32 *HC_RESTRICT order)
 {
-    HC_SHARED u32 hist[256];
-    const u32 tid = threadIdx.x;
-    if (tid < 256u) hist[tid] = 0;
+    // stable counting sort (file order inside a class, so the schedule is the same in every run): the
+    // files are cut in four quarters, thread (class, quarter) places the files of its class in its quarter
+    HC_SHARED u32 hist[4][256];
+    HC_SHARED u32 ctot[256];
+    const u32 tid = threadIdx.x, cls = tid & 255u, qtr = tid >> 8;
+    const u32 per = (nf + 3u) / 4u;
+    hist[qtr][cls] = 0;
     syncthreads();
-    for (u32 f = tid; f < nf; f += blockDim.x) {
-        const u64 v = len[f];
-        u32 cl = 0;
-        if (v) { const u32 lg = 63u - (u32)clzll(v); cl = 4u * lg + (u32)((lg >= 2u ? v >> (lg - 2u) : v << (2u - lg)) & 3u); }
-        atomic_add(&hist[cl > 255u ? 255u : cl], 1u);
-    }
+    for (u32 f = tid; f < nf; f += blockDim.x) atomic_add(&hist[f / per][fgk_len_class(len[f])], 1u);
+    syncthreads();
+    if (tid < 256u) ctot[tid] = hist[0][tid] + hist[1][tid] + hist[2][tid] + hist[3][tid];
     syncthreads();
     if (tid == 0) {
         u32 acc = 0;
-        for (int b = 255; b >= 0; b--) { const u32 h = hist[b]; hist[b] = acc; acc += h; }
+        for (int b = 255; b >= 0; b--) { const u32 h = ctot[b]; ctot[b] = acc; acc += h; }   // longest class first
     }
     syncthreads();
-    if (nf <= 65536u) {
-        // stable (file order inside a class, so the schedule is the same in every run): thread t places the
-        // files of class t
-        if (tid < 256u) {
-            u32 pos = hist[tid];
-            for (u32 f = 0; f < nf; f++) {
-                const u64 v = len[f];
-                u32 cl = 0;
-                if (v) { const u32 lg = 63u - (u32)clzll(v); cl = 4u * lg + (u32)((lg >= 2u ? v >> (lg - 2u) : v << (2u - lg)) & 3u); }
-                if ((cl > 255u ? 255u : cl) == tid) order[pos++] = f;
-            }
-        }
-        return;
-    }
-    for (u32 f = tid; f < nf; f += blockDim.x) {
-        const u64 v = len[f];
-        u32 cl = 0;
-        if (v) { const u32 lg = 63u - (u32)clzll(v); cl = 4u * lg + (u32)((lg >= 2u ? v >> (lg - 2u) : v << (2u - lg)) & 3u); }
-        order[atomic_add(&hist[cl > 255u ? 255u : cl], 1u)] = f;
-    }
+    u32 pos = ctot[cls];
+    for (u32 q = 0; q < qtr; q++) pos += hist[q][cls];
+    const u32 f1 = (qtr + 1u) * per < nf ? (qtr + 1u) * per : nf;
+    for (u32 f = qtr * per; f < f1; f++)
+        if (fgk_len_class(len[f]) == cls) order[pos++] = f;
 }
 
 // MSB-first bit writer: one 32-bit word per lane, 128-byte coalesced flushes
