@@ -394,19 +394,26 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
     const u8 *src = in + in_off[f];
     const AdaptHeader hd = ad_parse_header(src, m);
     if (hd.status) { if (lane == 0) { out_len[f] = 0; status[f] = hd.status; } return; }
-    if (!have_out) { if (lane == 0) { out_len[f] = hd.total; status[f] = 0; } return; }
-    if (hd.total > out_cap[f]) { if (lane == 0) { out_len[f] = hd.total; status[f] = 100; } return; }
-    if (hd.nb + 1 > blk_stride || m > 0xfffffff0ull) { if (lane == 0) { out_len[f] = hd.total; status[f] = AD_ST_SERIAL; } return; }
-    u32 *tab = blk_start + (u64)f * blk_stride;
+    // A token yields at most 255 bytes, so a header that promises more than 255 bytes per payload byte
+    // cannot be satisfied (a crafted w = h = 2^31 header would otherwise make the caller size its output
+    // for 2^62 bytes): such a stream is only walked for its exact error (13 or 14), nothing is sized or written.
+    const bool hopeless = hd.total > 255u * (m - 24u - hd.dir_bytes);
+    if (!have_out && !hopeless) { if (lane == 0) { out_len[f] = hd.total; status[f] = 0; } return; }
+    if (!hopeless) {
+        if (hd.total > out_cap[f]) { if (lane == 0) { out_len[f] = hd.total; status[f] = 100; } return; }
+        if (hd.nb + 1 > blk_stride || m > 0xfffffff0ull) { if (lane == 0) { out_len[f] = hd.total; status[f] = AD_ST_SERIAL; } return; }
+    }
+    u32 *tab = hopeless ? nullptr : blk_start + (u64)f * blk_stride;
     u64 pos = 24 + hd.dir_bytes;
     i32 err = 0;
     u64 blk = 0;
-    for (u64 by = 0; by < hd.h && !err; by += hd.b) {
-        const u64 bh = by + hd.b > hd.h ? hd.h - by : hd.b;
-        for (u64 bx = 0; bx < hd.w && !err; bx += hd.b, blk++) {
-            const u64 bw = bx + hd.b > hd.w ? hd.w - bx : hd.b;
-            const u64 req = bw * bh;
-            if (lane == 0) tab[blk] = (u32)pos;
+    // (crafted headers: block sides beyond 32 bits saturate the block size, offsets that would wrap end the loops)
+    for (u64 by = 0; by < hd.h && !err; by = by + hd.b < by ? hd.h : by + hd.b) {
+        const u64 bh = hd.h - by < hd.b ? hd.h - by : hd.b;
+        for (u64 bx = 0; bx < hd.w && !err; bx = bx + hd.b < bx ? hd.w : bx + hd.b, blk++) {
+            const u64 bw = hd.w - bx < hd.b ? hd.w - bx : hd.b;
+            const u64 req = (bw >> 32 || bh >> 32) ? ~0ull : bw * bh;
+            if (lane == 0 && tab) tab[blk] = (u32)pos;
             u64 produced = 0;
             u32 state = 0, prev_last = 0;
             while (produced < req) {
@@ -490,8 +497,8 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
         }
     }
     if (lane == 0) {
-        tab[hd.nb] = (u32)pos;
-        out_len[f] = hd.total;
+        if (tab) tab[hd.nb] = (u32)pos;
+        out_len[f] = hopeless ? 0 : hd.total;
         status[f] = err ? err : (pos != m ? 15 : 0);                    // src/transform.cpp:354-358
     }
 }
@@ -616,17 +623,28 @@ adapt_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, con
     // w*h cannot overflow here: nb <= 8m blocks of at most b*b... guard explicitly anyway
     if (h != 0 && w > ~0ull / h) { status[f] = 100; return; }
     const u64 total = w * h;
-    out_len[f] = total;
-    if (!out) { status[f] = 0; return; }
-    if (total > out_cap[f]) { status[f] = 100; return; }
-    u8 *mat = out + out_off[f];
+    // more than 255 bytes per payload byte cannot be satisfied (see adapt_index_kernel): walk for the
+    // exact error only, size and write nothing
+    const bool hopeless = total > 255u * (m - 24u - dir_bytes);
+    out_len[f] = hopeless ? 0 : total;
+    if (!out && !hopeless) { status[f] = 0; return; }
+    if (!hopeless && total > out_cap[f]) { status[f] = 100; return; }
+    u8 *mat = hopeless ? nullptr : out + out_off[f];
     u64 pos = 24 + dir_bytes;
     for (u64 i = 0; i < nb; i++) {
         const bool hor = (src[24 + (i >> 3)] >> (7 - (i & 7))) & 1u;
         BlockGeom g = ad_geom(w, h, b, i);
-        const u32 req = g.bw * g.bh, inner = hor ? g.bw : g.bh;
+        u64 req = (u64)g.bw * g.bh;
+        if (hopeless) {
+            // block sides beyond 32 bits (crafted headers only): saturate, the walk ends in 13 / 14 anyway
+            const u64 bx = (i % nbx) * b, by = (i / nbx) * b;
+            const u64 bw64 = bx + b > w ? w - bx : b, bh64 = by + b > h ? h - by : b;
+            req = (bw64 >> 32 || bh64 >> 32) ? ~0ull : bw64 * bh64;
+        }
+        const u32 inner = hor ? g.bw : g.bh;
         u8 *bp = mat + g.base;
-        u32 produced = 0, ci = 0, co = 0;
+        u64 produced = 0;
+        u32 ci = 0, co = 0;
         u32 match_byte = 0, match_count = 0;               // fresh state per block (:166-167)
         while (produced < req) {
             if (pos >= m) { status[f] = 14; return; }      // src/transform.cpp:170-174
@@ -638,7 +656,7 @@ adapt_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, con
                 if (match_byte == cur) match_count++; else { match_byte = cur; match_count = 1; }
             }
             if (produced + len > req) { status[f] = 13; return; }   // src/transform.cpp:180-184
-            for (u32 j = 0; j < len; j++) {
+            for (u32 j = 0; j < len && mat; j++) {
                 u64 a = hor ? (u64)co * w + ci : (u64)ci * w + co;
                 bp[a] = (u8)val;
                 if (++ci == inner) { ci = 0; co++; }

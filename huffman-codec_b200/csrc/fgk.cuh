@@ -3,30 +3,45 @@
 // swapNodes :186-217, drivers applyHuffman/revertHuffman src/transform.cpp:363-406, container
 // header src/headers.cpp:107-125 and bit packing src/main.cpp:78-84.
 //
-// The tree update is serial inside one stream, so the parallelism is the batch: ONE WARP PER
-// FILE with the tree in shared memory (9.9 KB per stream, 20 streams per SM).  All 32 lanes execute
-// the same control flow; lane 0 is the only writer of links.  The kernel is bound by the chain of
-// dependent instructions of one warp (a lone high-entropy stream is only 15-20 % faster than the
-// whole batch), so everything is arranged to shorten that chain: a PATH TABLE (below, at FgkTree)
-// lets the 32 lanes look at all levels of a root->leaf path at once, and the layout makes the
-// per-level work of the remaining sequential walks as few instructions as possible:
+// The tree update is serial inside one stream, so the parallelism is the batch: ONE WARP PER FILE
+// with the tree in shared memory (8.7 KB per stream).  A lone stream is bound by the chain of
+// dependent instructions of its warp, a full batch by instruction issue (7 warps per scheduler),
+// so both the chain and the instruction count matter.  Measured on B200 (tools/ubench_latency.cu):
+// LDS 24 cycles, SHFL 33, ballot 25, ballot -> clz -> shfl 73, REDUX 28.
 //
-//   slot = node number 0..512: siblings adjacent, even slot = left child = bit 0,
-//   weights non-decreasing in slot order, so the block leader of s is the last slot l >= s with
-//   w[l] == w[s].
-//   up[s]   = { weight, SHARED-MEMORY ADDRESS of up[parent(s)] }   one LDS.64, no address math
-//   down[s] = internal: shared address of down[left child]; leaf: (symbol << 1) | 1
-//   The code bit of slot s is bit 3 of the address of up[s] (8-byte entries, 16-byte aligned base).
+//   node handle = byte offset o = 8 * node number: siblings adjacent, even number =
+//   left child = bit 0, weights non-decreasing in number order, so the block leader of a node is the
+//   last node l >= it with the same weight.
+//   rec[o / 8] = { weight, parent offset | down << 16 }      one LDS.64 per node
+//       down   = internal: offset of the left child;  leaf: 0x8000 | symbol (NYT: 0x8100)
+//   The root's weight is never consulted by the algorithm except as "the node after 511", where a
+//   tie can only mean "the leader is my parent" = no swap; it is kept at 0xffffffff (never ties).
+//   PATH TABLE  pt[(2 << j) - 2 + p] = offset of the node reached from the root by the (j+1)-bit
+//   path p (FGK_ROOT_O: none), for the top FGK_D levels; pfx[node] = depth << 12 | path, the path
+//   LEFT ALIGNED in 9 bits (0xffff for deeper nodes).  The table describes node NUMBERS, so the most
+//   frequent swap -- two leaves exchange their symbols -- leaves it valid.
+//   spf[symbol] = leaf offset | pfx of that leaf << 16: one load gives the encoder a symbol's code.
 //
-//   sequential walk, per level: LDS.64 up[s], LDS.32 up[s+1].w -> if the weights differ (common
-//   case) there is no leader to find: lane 0 stores w+1 and the walk follows the parent address.
-//   Only when they are equal the warp probes 32 slots per ballot for the leader and, if needed,
-//   swaps the two subtrees.  Used for nodes deeper than the path table; there encoding collects the
-//   code bits on the same walk (shifted in from the top, a marker bit tracks the length) until
-//   the first swap, after which the old path is finished alongside the rest of the update.
+//   One symbol (fgk_update_rounds): lane j owns the node at depth j + 1 of the leaf's path.  ROUND:
+//   every lane loads its node, the next node and the weight after that in one batch of independent
+//   loads, decides locally "tie with the next node -> leader search / swap needed" and what the swap
+//   would be, and ONE REDUX.MAX over (lane << 27 | swap description) tells all lanes the deepest
+//   tied level, whether it swaps, and the path of the leader.  The lanes below it store weight + 1,
+//   the tied lane does its own swap stores, and only if the walk moved to another branch the lanes
+//   look up the new path (one table load) and start the next round.  A run of three or more equal
+//   weights (2/3 of all ties on high-entropy data) is resolved by all lanes together: a second
+//   REDUX (issued with the first) carries the tied node's offset, 32 lanes probe the run in one
+//   load + ballot, and the swap is then described by uniform loads -- no shuffles anywhere.
+//   Nodes deeper than the table and first occurrences (NYT split) use sequential code (fgk_update_seq).
 //
-// Bits are packed MSB-first into 32-bit words; each lane keeps one word and the warp flushes
-// 128 bytes at a time (coalesced).  The 9-byte container header goes through the same writer.
+//   Nothing written in a round is read again in a later round of the same symbol (parents, leaders
+//   and probes all have larger numbers than what was written), every load of a round is separated
+//   from the round's stores by a warp barrier, and one warp barrier per symbol publishes the stores.
+//
+// Encoder bit output: a table code (<= 9 bits) is parked in the lane whose index is the symbol
+// count mod 32; every 32 symbols the warp packs them at once (shuffle scan of the lengths, shared
+// memory atomic OR into a 64-word ring, 128-byte coalesced flushes).  Long codes and the 9-byte
+// container header go through the same ring serially.
 #pragma once
 #include "hc_common.cuh"
 
@@ -38,126 +53,144 @@ namespace hcd {
 #ifndef HC_FGK_DEC_WARPS
 #define HC_FGK_DEC_WARPS 4
 #endif
-// streams per CTA.  Measured on C3 (final kernels): encoder 1 / 2 / 3 / 4 -> 152 / 178-186 / 183 / 174 ms, decoder
-// 1 / 2 / 4 -> 205 / 201 / 198 ms.  One-warp CTAs give their 9.9 KB back as soon as their stream ends.
+// streams per CTA (one-warp CTAs give their shared memory back as soon as their stream ends)
 constexpr int FGK_ENC_WARPS = HC_FGK_ENC_WARPS;
 constexpr int FGK_DEC_WARPS = HC_FGK_DEC_WARPS;
 constexpr int FGK_WARPS = FGK_ENC_WARPS > FGK_DEC_WARPS ? FGK_ENC_WARPS : FGK_DEC_WARPS;
-constexpr u32 FGK_ROOT = 512;
-constexpr u32 FGK_NSLOT = 514;           // slots 0..512 + one sentinel (weight 0xffffffff)
-constexpr u32 FGK_LEAF_NYT = (256u << 1) | 1u;
+constexpr u32 FGK_NREC = 516;                    // nodes 0..512, sentinel 513, two pad records
+constexpr u32 FGK_ROOT_O = 8u * 512u;            // also "no node" in pt (the root itself is never listed)
+constexpr u32 FGK_SENT_O = 8u * 513u;            // weight 0xffffffff: ends every leader search
+constexpr u32 FGK_NONE_O = 8u * 515u;            // leaf offset of a symbol not yet transmitted
+constexpr u32 FGK_LEAF = 0x8000u;
+constexpr u32 FGK_LEAF_NYT = 0x8100u;
 constexpr u32 FGK_D = 9;                         // levels covered by the path table
 constexpr u32 FGK_PT_N = (2u << FGK_D) - 2u;     // 2 + 4 + ... + 2^D entries
 constexpr u32 FGK_NOPATH = 0xffffu;
+constexpr u32 FGK_SPF_NONE = FGK_NONE_O | (FGK_NOPATH << 16);
 
-// PATH TABLE.  pt[(1 << d) - 2 + p] = slot + 1 of the node reached from the root by the d-bit path p
-// (0: no such node), for d = 1..FGK_D; pfx[slot] = d << 12 | p for those nodes (FGK_NOPATH for
-// deeper ones).  With it the nodes of a root->leaf path are found by 32 lanes AT ONCE (one lookup
-// per level) instead of by a chain of dependent loads: decoding reads the next FGK_D code bits and
-// knows every node on the way; encoding takes the code of a leaf straight from pfx; and the
-// update's "does this level need a swap" test runs for all levels of the path in one ballot.
-// The table describes SLOTS, so the most frequent swap (two leaves exchange their symbols) leaves it
-// valid; a swap that moves an internal node re-derives the entries below the two slots (warp-parallel,
-// level by level), an NYT split adds its two entries.  Deeper levels fall back to the sequential walks.
 struct HC_ALIGNED16 FgkTree {
-    uint2 up[FGK_NSLOT];     // {weight, shared address of the parent's up entry}
-    u32 down[FGK_NSLOT];     // see above
-    u16 slot_of[256];        // leaf slot of a symbol, 0xffff = not yet transmitted
+    uint2 rec[FGK_NREC];     // {weight, parent | down << 16}
+    u32 spf[256];            // leaf offset | pfx << 16 of a symbol, FGK_SPF_NONE = not yet transmitted
+    u16 pfx[FGK_NREC];       // depth << 12 | left-aligned path
     u16 pt[FGK_PT_N + 2];
-    u16 pfx[FGK_NSLOT + 2];
-    u8 buf[128];             // staging of 128 symbols (one coalesced transfer)
+    u32 ring[64];            // encoder: bit output ring (two halves of 32 words)
+    u8 buf[256];             // symbol staging: two halves of 128 (encoder: ring; decoder: first half)
     u8 pad[8];
 };
 
+static_assert(sizeof(FgkTree) % 16 == 0, "trees are 16-byte aligned");
 static_assert(sizeof(FgkTree) * FGK_WARPS <= 48u * 1024u, "the trees of a CTA are static shared memory");
 
-struct FgkCtx {              // shared addresses, identical in every lane
-    u32 up, down, slot_of, buf, root, sentinel, nyt;
-    u32 pt, pfx, lev;        // lev: number of populated levels of pt
-    u32 fl;                  // out-of-line helpers: bit 0 = the watched leaf moved
+struct FgkCtx {              // shared addresses (identical in every lane) + per-lane table constants
+    u32 rec, spf, pfx, pt, buf, ring;
+    u32 nyt;                 // offset of the NYT node
+    u32 lev;                 // number of populated levels of pt
+    u32 gen;                 // bumped whenever pt may have changed (the decoder's prefetched lookup is then redone)
+    u32 err;                 // set when a walk does not end (cannot happen on a consistent tree): the stream fails with status 102
+    u32 ptj, shj;            // lane j: address of its level of pt, shift that turns a left-aligned path into its index
 };
+
+HC_DEV u32 fgk_parent(u32 pd) { return pd & 0xffffu; }
+HC_DEV u32 fgk_down(u32 pd) { return pd >> 16; }
 
 HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
 {
-    c.up = smem_addr(&t.up[0]);
-    c.down = smem_addr(&t.down[0]);
-    c.slot_of = smem_addr(&t.slot_of[0]);
-    c.buf = smem_addr(&t.buf[0]);
-    c.root = c.up + 8u * FGK_ROOT;
-    c.sentinel = c.up + 8u * (FGK_ROOT + 1u);
-    c.nyt = c.root;
-    c.pt = smem_addr(&t.pt[0]);
+    c.rec = smem_addr(&t.rec[0]);
+    c.spf = smem_addr(&t.spf[0]);
     c.pfx = smem_addr(&t.pfx[0]);
+    c.pt = smem_addr(&t.pt[0]);
+    c.buf = smem_addr(&t.buf[0]);
+    c.ring = smem_addr(&t.ring[0]);
+    c.nyt = FGK_ROOT_O;
     c.lev = 0;
-    c.fl = 0;
-    for (u32 i = lane; i < 128u; i += 32) sts32(c.slot_of + 4u * i, 0xffffffffu);
-    for (u32 i = lane; i < (FGK_PT_N + 2u) / 2u; i += 32) sts32(c.pt + 4u * i, 0u);
-    for (u32 i = lane; i < (FGK_NSLOT + 2u) / 2u; i += 32) sts32(c.pfx + 4u * i, 0xffffffffu);
+    c.gen = 0;
+    c.err = 0;
+    c.ptj = c.pt + (lane < FGK_D ? 2u * ((2u << lane) - 2u) : 0u);
+    c.shj = lane < FGK_D ? FGK_D - 1u - lane : 0u;
+    for (u32 i = lane; i < 256u; i += 32) sts32(c.spf + 4u * i, FGK_SPF_NONE);
+    for (u32 i = lane; i < (FGK_PT_N + 2u) / 2u; i += 32) sts32(c.pt + 4u * i, FGK_ROOT_O | (FGK_ROOT_O << 16));
+    for (u32 i = lane; i < FGK_NREC / 2u; i += 32) sts32(c.pfx + 4u * i, 0xffffffffu);
+    sts32(c.ring + 4u * lane, 0u);
+    sts32(c.ring + 128u + 4u * lane, 0u);
     if (lane == 0) {
-        uint2 z; z.x = 0; z.y = 0;
-        sts64(c.root, z);
-        z.x = 0xffffffffu;
-        sts64(c.sentinel, z);
-        sts32(c.down + 4u * FGK_ROOT, FGK_LEAF_NYT);
+        uint2 z; z.x = 0xffffffffu; z.y = FGK_LEAF_NYT << 16;
+        sts64(c.rec + FGK_ROOT_O, z);
+        z.y = 0;
+        sts64(c.rec + FGK_SENT_O, z);
+        sts64(c.rec + FGK_SENT_O + 8u, z);
+        sts64(c.rec + FGK_SENT_O + 16u, z);
     }
     syncwarp();
 }
 
-HC_DEV u32 fgk_down_of(const FgkCtx &c, u32 a) { return c.down + ((a - c.up) >> 1); }   // up address -> down address
-HC_DEV u32 fgk_up_of(const FgkCtx &c, u32 d) { return c.up + ((d - c.down) << 1); }
+// per-lane node of a path: lane j < depth gets the offset of the node at depth j + 1.  The other
+// lanes get whatever lies along the bits below it, or the root; callers mask them by depth.
+HC_DEV u32 fgk_lookup(const FgkCtx &c, u32 pf)
+{
+    return lds16(c.ptj + 2u * ((pf & 0x1ffu) >> c.shj));
+}
+
+// pfx of a node; a leaf's symbol entry carries a copy
+HC_DEV void fgk_set_pfx(const FgkCtx &c, u32 o, u32 pf)
+{
+    sts16(c.pfx + (o >> 2), pf);
+    const u32 kd = fgk_down(lds32(c.rec + o + 4u));
+
+    if ((kd & FGK_LEAF) && kd != FGK_LEAF_NYT) sts16(c.spf + 4u * (kd & 0xffu) + 2u, pf);
+}
 
 // Rebuilds the path table from the tree, one level per step, the nodes of a level spread over the
 // lanes.  Called by all lanes after the tree changed shape.
 HC_DEV void fgk_rebuild(FgkCtx &c, u32 lane)
 {
-    syncwarp();                                           // the tree writes of lane 0 are visible
-    for (u32 sl = ((c.nyt - c.up) >> 3) + lane; sl <= FGK_ROOT; sl += 32) sts16(c.pfx + 2u * sl, FGK_NOPATH);
+    syncwarp();                                           // the tree writes are visible
+    for (u32 o = c.nyt + 8u * lane; o < FGK_ROOT_O; o += 256u) fgk_set_pfx(c, o, FGK_NOPATH);
     syncwarp();
     u32 lev = 0;
     for (u32 d = 1; d <= FGK_D; d++) {
         const u32 base = (1u << d) - 2u, pbase = (1u << (d - 1u)) - 2u;
         u32 any = 0;
         for (u32 p = lane; p < (1u << d); p += 32) {
-            const u32 pe = d == 1u ? FGK_ROOT + 1u : lds16(c.pt + 2u * (pbase + (p >> 1)));
-            u32 e = 0;
-            if (pe) {
-                const u32 kd = lds32(c.down + 4u * (pe - 1u));
-                if (!(kd & 1u)) e = ((kd - c.down) >> 2) + (p & 1u) + 1u;     // slot + 1 of the child
+            const u32 pe = d == 1u ? FGK_ROOT_O : lds16(c.pt + 2u * (pbase + (p >> 1)));
+            u32 e = FGK_ROOT_O;
+            if (d == 1u || pe != FGK_ROOT_O) {
+                const u32 kd = fgk_down(lds32(c.rec + pe + 4u));
+                if (!(kd & FGK_LEAF)) e = kd + 8u * (p & 1u);                 // the child
             }
             sts16(c.pt + 2u * (base + p), e);
-            if (e) sts16(c.pfx + 2u * (e - 1u), (d << 12) | p);
-            any |= e;
+            if (e != FGK_ROOT_O) { fgk_set_pfx(c, e, (d << 12) | (p << (FGK_D - d))); any = 1; }
         }
         syncwarp();
         if (ballot(any != 0u) == 0u) {
             // level d is empty (and written as such); clear what an earlier, deeper tree left below
             for (u32 d2 = d + 1u; d2 <= c.lev; d2++)
-                for (u32 p = lane; p < (1u << d2); p += 32) sts16(c.pt + 2u * ((1u << d2) - 2u + p), 0u);
+                for (u32 p = lane; p < (1u << d2); p += 32) sts16(c.pt + 2u * ((1u << d2) - 2u + p), FGK_ROOT_O);
             break;
         }
         lev = d;
     }
     c.lev = lev;
+    c.gen++;
     syncwarp();
 }
 
-// After slots x and y exchanged their subtrees only the table entries BELOW them change (the slots
-// keep their own paths).  px / py = their pfx entries (FGK_NOPATH: that slot lies deeper than the
-// table, nothing below it is listed).  First every node listed below either slot loses its path,
+// After nodes x and y exchanged their subtrees only the table entries BELOW them change (the nodes
+// keep their own paths).  px / py = their pfx entries (FGK_NOPATH: that node lies deeper than the
+// table, nothing below it is listed).  First every node listed below either one loses its path,
 // then both ranges are re-derived level by level.
 HC_DEV void fgk_rebuild_pair(FgkCtx &c, u32 px, u32 py, u32 lane)
 {
-    syncwarp();                                           // the tree writes of lane 0 are visible
+    syncwarp();                                           // the tree writes are visible
 #pragma unroll 1
     for (u32 side = 0; side < 2u; side++) {
         const u32 pf = side ? py : px;
         if (pf == FGK_NOPATH) continue;
-        const u32 depth = pf >> 12, path = pf & 0xfffu;
+        const u32 depth = pf >> 12, path = (pf & 0x1ffu) >> (FGK_D - depth);
         for (u32 d = depth + 1u; d <= FGK_D; d++) {
             const u32 n = 1u << (d - depth), base = (1u << d) - 2u + (path << (d - depth));
             for (u32 i = lane; i < n; i += 32) {
                 const u32 e = lds16(c.pt + 2u * (base + i));
-                if (e) sts16(c.pfx + 2u * (e - 1u), FGK_NOPATH);
+                if (e != FGK_ROOT_O) fgk_set_pfx(c, e, FGK_NOPATH);
             }
         }
     }
@@ -167,7 +200,7 @@ HC_DEV void fgk_rebuild_pair(FgkCtx &c, u32 px, u32 py, u32 lane)
     for (u32 side = 0; side < 2u; side++) {
         const u32 pf = side ? py : px;
         if (pf == FGK_NOPATH) continue;
-        const u32 depth = pf >> 12, path = pf & 0xfffu;
+        const u32 depth = pf >> 12, path = (pf & 0x1ffu) >> (FGK_D - depth);
         for (u32 d = depth + 1u; d <= FGK_D; d++) {
             const u32 n = 1u << (d - depth), p0 = path << (d - depth);
             const u32 base = (1u << d) - 2u, pbase = (1u << (d - 1u)) - 2u;
@@ -175,14 +208,13 @@ HC_DEV void fgk_rebuild_pair(FgkCtx &c, u32 px, u32 py, u32 lane)
             for (u32 i = lane; i < n; i += 32) {
                 const u32 p = p0 + i;
                 const u32 pe = lds16(c.pt + 2u * (pbase + (p >> 1)));
-                u32 e = 0;
-                if (pe) {
-                    const u32 kd = lds32(c.down + 4u * (pe - 1u));
-                    if (!(kd & 1u)) e = ((kd - c.down) >> 2) + (p & 1u) + 1u;
+                u32 e = FGK_ROOT_O;
+                if (pe != FGK_ROOT_O) {
+                    const u32 kd = fgk_down(lds32(c.rec + pe + 4u));
+                    if (!(kd & FGK_LEAF)) e = kd + 8u * (p & 1u);
                 }
                 sts16(c.pt + 2u * (base + p), e);
-                if (e) sts16(c.pfx + 2u * (e - 1u), (d << 12) | p);
-                any |= e;
+                if (e != FGK_ROOT_O) { fgk_set_pfx(c, e, (d << 12) | (p << (FGK_D - d))); any = 1; }
             }
             syncwarp();
             if (ballot(any != 0u) && d > lev) lev = d;
@@ -191,310 +223,304 @@ HC_DEV void fgk_rebuild_pair(FgkCtx &c, u32 px, u32 py, u32 lane)
     c.lev = lev;
 }
 
-// table entries of the two slots created by an NYT split of slot n (up address); pn = pfx of n
-// before the split, or depth 0 for the root
+// out-of-line form for the update's hot loop (an internal node moves about once per 100 symbols)
+HC_DEV_NOINLINE u32 fgk_rebuild_pair_cold(FgkCtx c, u32 px, u32 py, u32 lane)
+{
+    fgk_rebuild_pair(c, px, py, lane);
+    return c.lev;
+}
+
+// table entries of the two nodes created by an NYT split of node n; pn = pfx of n before the
+// split (depth 0 for the root)
 HC_DEV void fgk_table_split(FgkCtx &c, u32 n, u32 pn, u32 lane)
 {
-    if (pn == FGK_NOPATH) return;                         // deeper than the table: the new slots stay unlisted
-    const u32 depth = pn >> 12, path = pn & 0xfffu;
+    if (pn == FGK_NOPATH) return;                         // deeper than the table: the new nodes stay unlisted
+    const u32 depth = pn >> 12, path = (pn & 0x1ffu) >> (FGK_D - depth);
     if (depth >= FGK_D) return;
-    const u32 d = depth + 1u, sl = (n - c.up) >> 3;       // children: slots sl-2 (bit 0) and sl-1 (bit 1)
+    const u32 d = depth + 1u;                             // children: n - 16 (bit 0) and n - 8 (bit 1)
     if (lane < 2u) {
-        const u32 p = (path << 1) | lane, child = sl - 2u + lane;
-        sts16(c.pt + 2u * ((1u << d) - 2u + p), child + 1u);
-        sts16(c.pfx + 2u * child, (d << 12) | p);
+        const u32 p = (path << 1) | lane, child = n - 16u + 8u * lane;
+        sts16(c.pt + 2u * ((1u << d) - 2u + p), child);
+        fgk_set_pfx(c, child, (d << 12) | (p << (FGK_D - d)));
     }
     if (d > c.lev) c.lev = d;
+    c.gen++;
     syncwarp();
 }
 
-// NYT split (src/huffman.cpp:99-111): the NYT slot n becomes internal with children n-2 (new NYT)
-// and n-1 (leaf of `sym`).  Returns the up address of the new leaf.
+// NYT split (src/huffman.cpp:99-111): the NYT node n becomes internal with children n-2 (new NYT)
+// and n-1 (leaf of `sym`).  Returns the offset of the new leaf.
 HC_DEV u32 fgk_split(FgkCtx &c, u32 sym, u32 lane)
 {
-    const u32 n = c.nyt;                      // up address of the current NYT
-    syncwarp();                               // every lane has done its slot_of / nyt-path reads
+    const u32 n = c.nyt;
+    syncwarp();                               // every lane has done its reads of the old tree
     if (lane == 0) {
-        uint2 z; z.x = 0; z.y = n;
-        sts64(n - 8u, z);                     // leaf  (slot n-1): weight 0, parent n
-        sts64(n - 16u, z);                    // NYT   (slot n-2)
-        const u32 dn = fgk_down_of(c, n);
-        sts32(dn, dn - 8u);                   // internal: address of the left child's down entry
-        sts32(dn - 4u, (sym << 1) | 1u);
-        sts32(dn - 8u, FGK_LEAF_NYT);
-        sts16(c.slot_of + 2u * sym, ((n - c.up) >> 3) - 1u);
+        uint2 z; z.x = 0; z.y = n | ((FGK_LEAF | sym) << 16);
+        sts64(c.rec + n - 8u, z);             // leaf: weight 0, parent n
+        z.y = n | (FGK_LEAF_NYT << 16);
+        sts64(c.rec + n - 16u, z);            // new NYT
+        sts16(c.rec + n + 6u, n - 16u);       // n is internal now: its left child
+        sts32(c.spf + 4u * sym, (n - 8u) | (FGK_NOPATH << 16));
     }
     c.nyt = n - 16u;
     syncwarp();
     return n - 8u;
 }
 
-// collect one code bit (bit 3 of the up address) at the top of the 64-bit accumulator hi:lo
-HC_DEV void fgk_code_bit(u32 a, u32 &hi, u32 &lo)
+// collect one code bit (node number odd = right child = 1) at the top of the 64-bit accumulator hi:lo
+HC_DEV void fgk_code_bit(u32 o, u32 &hi, u32 &lo)
 {
     lo = funnel_r(lo, hi, 1);
-    hi = (hi >> 1) | ((a << 28) & 0x80000000u);
+    hi = (hi >> 1) | ((o << 28) & 0x80000000u);
 }
 
-// Ordering of lane 0's weight store against the other lanes' reads of the same level.  On the
-// GPU a converged warp executes the predicated store after the (earlier) load instruction of all
-// lanes, so the product build adds nothing; -DHC_FGK_STRICT (and the emulator) insert a warp
-// barrier per level for tools that check the CUDA memory model formally (racecheck).
-#if defined(HC_EMU) || defined(HC_FGK_STRICT)
-#define FGK_LEVEL_SYNC() syncwarp()
-#else
-#define FGK_LEVEL_SYNC() ((void)0)
-#endif
-
-// `sc` (structure changed) is set when the swap moved an internal node.
-// slow path of one level: w[s+1] == w[s].  Finds the block leader (32 slots per ballot) and swaps
-// the subtrees if required (src/huffman.cpp:115-122).  Returns true if a swap happened; a / parent
-// are updated to the slot the node now occupies.  `watch` is the next symbol to be coded: if its
-// leaf moves, *moved is set so that the caller refreshes its prefetched slot.
-HC_DEV bool fgk_leader_swap(FgkCtx &c, u32 &a, u32 &parent, u32 ws, u32 lane, u32 watch, bool &moved, bool &sc)
+// code of node o in the current tree: parent chase to the root.  hi:lo enter as 0x80000000:0 (the
+// marker bit ends up below the last code bit).
+HC_DEV void fgk_code_of(const FgkCtx &c, u32 o, u32 &hi, u32 &lo)
 {
-    u32 l = a + 8u;
-    // the common short block: one more plain load decides it without a ballot
-    if (lds32(a + 16u) == ws) {
-        u32 run;
-        l = a;
-        do {
-            u32 pa = l + 8u * (1u + lane);
-            pa = pa < c.sentinel ? pa : c.sentinel;
-            u32 m = ~ballot(lds32(pa) == ws);
-            run = m ? (u32)ffs(m) - 1u : 32u;
-            l += 8u * run;
-        } while (run == 32u);
-    }
-    if (l == parent) return false;
-    // exchange the contents of slots a and l; every lane reads, lane 0 writes
-    const u32 da = fgk_down_of(c, a), dl = fgk_down_of(c, l);
-    const u32 ka = lds32(da), kl = lds32(dl);
-    syncwarp();
-    if (lane == 0) {
-        sts32(da, kl);
-        sts32(dl, ka);
-        if (!(kl & 1u)) { u32 cu = fgk_up_of(c, kl); sts32(cu + 4u, a); sts32(cu + 12u, a); }
-        else if (kl != FGK_LEAF_NYT) sts16(c.slot_of + (kl & ~1u), (a - c.up) >> 3);
-        if (!(ka & 1u)) { u32 cu = fgk_up_of(c, ka); sts32(cu + 4u, l); sts32(cu + 12u, l); }
-        else if (ka != FGK_LEAF_NYT) sts16(c.slot_of + (ka & ~1u), (l - c.up) >> 3);
-    }
-    if (kl == FGK_LEAF_NYT) c.nyt = a;
-    if (ka == FGK_LEAF_NYT) c.nyt = l;
-    if (!(ka & kl & 1u)) sc = true;                       // an internal node moved: the path table is stale
-    const u32 wleaf = (watch << 1) | 1u;
-    if (ka == wleaf || kl == wleaf) moved = true;
-    a = l;
-    parent = lds32(l + 4u);
-    return true;
+    for (u32 guard = 0; o < FGK_ROOT_O && guard < 600u; guard++, o = fgk_parent(lds32(c.rec + o + 4u))) fgk_code_bit(o, hi, lo);
 }
 
-// FGK update from the node at up address a (src/huffman.cpp:113-127); `count` = symbols processed
-// including this one (= the new root weight).  Nothing written at one level is read again at a
-// higher level of the same walk (parents, leaders and probes all have larger slot numbers); the
-// barrier at the end publishes lane 0's writes before the next symbol.  The parent's entry is
-// fetched one level ahead (software pipelining of the dependent shared-memory loads).
-HC_DEV void fgk_update_plain(FgkCtx &c, u32 a, u32 lane, u32 count, u32 watch, bool &moved, bool &sc)
+// last node of the run of weight W: `from` = first candidate (the nodes before it are known to carry W)
+HC_DEV u32 fgk_leader(const FgkCtx &c, u32 from, u32 W, u32 lane)
 {
-    const bool w0 = lane == 0;
-    if (a != c.root) {
-        uint2 n = lds64(a);
-        u32 w1 = lds32(a + 8u);
-        // two levels per iteration so that the prefetched entry (pn / n) alternates between two
-        // register sets instead of being copied every level
-        for (;;) {
-            u32 p = n.y;                                   // level A: node a, entry n
-            uint2 pn = lds64(p);
-            u32 pw1 = lds32(p + 8u);
-            if (w1 == n.x && fgk_leader_swap(c, a, p, n.x, lane, watch, moved, sc)) {
-                pn = lds64(p);
-                pw1 = lds32(p + 8u);
+    u32 run;
+    do {
+        u32 pa = from + 8u * lane;
+        pa = pa < FGK_SENT_O ? pa : FGK_SENT_O;
+        const u32 m = ~ballot(lds32(c.rec + pa) == W);
+        run = m ? (u32)ffs(m) - 1u : 32u;
+        from += 8u * run;
+    } while (run == 32u);
+    return from - 8u;
+}
+
+// re-attach what hangs below a node that moved to offset `to` (whose pfx is pf_to): a leaf's symbol
+// entry, or the parent links of the two children
+HC_DEV void fgk_relink(const FgkCtx &c, u32 k, u32 to, u32 pf_to)
+{
+    if (k & FGK_LEAF) {
+        if (k != FGK_LEAF_NYT) sts32(c.spf + 4u * (k & 0xffu), to | (pf_to << 16));
+    } else {
+        sts16(c.rec + k + 4u, to);
+        sts16(c.rec + k + 12u, to);
+    }
+}
+
+// Sequential FGK update from node a (src/huffman.cpp:113-127): all lanes walk together, lane 0
+// writes.  For the rare callers: nodes deeper than the path table, the first occurrence of a symbol,
+// the continuation after a swap with such a node.  Out of line (one copy instead of one per call
+// site keeps the kernels inside the instruction cache); the context travels by value so that the
+// caller's copy can stay in registers.
+HC_DEV_NOINLINE FgkCtx fgk_update_seq(FgkCtx c, u32 a, u32 lane)
+{
+    bool sc = false;
+    u32 guard = 0;
+    while (a != FGK_ROOT_O) {
+        if (++guard > 600u || a > FGK_ROOT_O) { c.err = 1; return c; }     // more levels than nodes: never on a consistent tree
+        const uint2 r = lds64(c.rec + a);
+        const u32 W = r.x;
+        u32 parent = fgk_parent(r.y);
+        u32 l = a;
+        if (lds32(c.rec + a + 8u) == W) l = fgk_leader(c, a + 16u, W, lane);
+        syncwarp();                                   // every lane has read this level
+        if (l != a && l != parent) {
+            // exchange the contents of a and l (src/huffman.cpp:186-217)
+            const u32 ka = fgk_down(r.y), pl = lds32(c.rec + l + 4u), kl = fgk_down(pl);
+            const u32 pfa = lds16(c.pfx + (a >> 2)), pfl = lds16(c.pfx + (l >> 2));
+            syncwarp();
+            if (lane == 0) {
+                sts16(c.rec + a + 6u, kl);
+                sts16(c.rec + l + 6u, ka);
+                fgk_relink(c, kl, a, pfa);
+                fgk_relink(c, ka, l, pfl);
             }
-            FGK_LEVEL_SYNC();
-            sts32_if(w0, a, n.x + 1u);
-            if (p == c.root) break;
-            a = pn.y;                                      // level B: node p, entry pn
-            n = lds64(a);
-            w1 = lds32(a + 8u);
-            if (pw1 == pn.x && fgk_leader_swap(c, p, a, pn.x, lane, watch, moved, sc)) {
-                n = lds64(a);
-                w1 = lds32(a + 8u);
-            }
-            FGK_LEVEL_SYNC();
-            sts32_if(w0, p, pn.x + 1u);
-            if (a == c.root) break;
+            if (kl == FGK_LEAF_NYT) c.nyt = a;
+            if (ka == FGK_LEAF_NYT) c.nyt = l;
+            if (!(ka & kl & FGK_LEAF)) sc = true;     // an internal node moved: the path table is stale
+            a = l;
+            parent = fgk_parent(pl);
         }
+        if (lane == 0) sts32(c.rec + a, W + 1u);
+        a = parent;
+        syncwarp();
     }
-    sts32_if(w0, c.root, count);
-    syncwarp();
-}
-
-// Out-of-line forms of the sequential walks for the rare callers (nodes deeper than the path table,
-// the first occurrence of a symbol): one copy of the code instead of one per call site keeps the
-// kernels inside the instruction cache.  The context travels by value so that the caller's copy can
-// stay in registers; the full table rebuild is included.
-HC_DEV_NOINLINE FgkCtx fgk_update_plain_cold(FgkCtx c, u32 a, u32 lane, u32 count, u32 watch)
-{
-    bool moved = false, sc = false;
-    fgk_update_plain(c, a, lane, count, watch, moved, sc);
     if (sc) fgk_rebuild(c, lane);
-    c.fl = moved ? 1u : 0u;
     return c;
 }
 
-// FGK update of node a whose path is in the table (pf = its pfx entry): lane j takes the node at
-// depth j + 1, one ballot tells which levels need the leader search.  Levels below the deepest such
-// level are plain increments and done at once; that level is handled by fgk_leader_swap, after which
-// the walk continues from the (possibly new) parent with a fresh table lookup.
-// A1 (optional, first round only): the caller already knows the node of every level (decode found
-// them while resolving the code) -- lane j holds the up address of the node at depth j + 1.
-// W1 / W1n: the weights of that node and of the slot after it, fetched by the caller together with
-// its own lookups (lanes without a level hold the root, which never ties).
-HC_DEV void fgk_update_fast(FgkCtx &c, u32 a, u32 pf, u32 lane, u32 count, u32 watch, bool &moved, bool have_a1 = false,
-                            u32 A1 = 0, u32 W1 = 0, u32 W1n = 0)
+// what a tied lane tells the others through the REDUX (larger lane = deeper level wins)
+constexpr u32 FGK_I_NOSWAP = 1u << 16;    // the leader is the node's parent: plain increment
+constexpr u32 FGK_I_SAMEP = 1u << 17;     // leader and node share the parent: the path above is unchanged
+constexpr u32 FGK_I_SC = 1u << 18;        // an internal node moves: table entries below the two nodes change
+constexpr u32 FGK_I_LONG = 1u << 20;      // more than two equal weights: leader search
+constexpr u32 FGK_I_TIE = 1u << 26;
+
+struct FgkPre {          // what a lane loads about its node A per round
+    uint2 n;             // rec[A]
+    uint2 n1;            // rec[A + 8]
+    u32 w2;              // weight of A + 16
+    u32 pfl;             // pfx[A + 8]
+};
+
+HC_DEV FgkPre fgk_preload(const FgkCtx &c, u32 A)
 {
-    for (;;) {
-        if (pf == FGK_NOPATH) {                           // deeper than the table: sequential walk
-            c = fgk_update_plain_cold(c, a, lane, count, watch);
-            if (c.fl & 1u) moved = true;
-            return;
-        }
-        const u32 depth = pf >> 12, path = pf & 0xfffu;
-        const bool valid = lane < depth;
-        u32 A = c.root;                                   // idle lanes: the root never ties (sentinel above it)
-        u32 W, w1;
-        if (have_a1) {
-            A = A1; W = W1; w1 = W1n;
-            have_a1 = false;
-        } else {
-            if (valid) {
-                A = a;
-                if (lane + 1u < depth) A = c.up - 8u + 8u * lds16(c.pt + 2u * ((2u << lane) - 2u + (path >> (depth - 1u - lane))));
-            }
-            W = lds32(A);
-            w1 = lds32(A + 8u);
-        }
-        const u32 tm = ballot(valid && w1 == W);
-        FGK_LEVEL_SYNC();
-        if (tm == 0u) {
-            sts32_if(valid, A, W + 1u);
-            sts32_if(lane == 0, c.root, count);
-            syncwarp();
-            return;
-        }
-        const u32 k0 = 31u - (u32)clz(tm);                // deepest level with a tie
-        sts32_if(valid && lane > k0, A, W + 1u);          // plain levels below it
-        u32 ak = shfl(A, (int)k0);
-        const u32 wk = shfl(W, (int)k0);
-        u32 parent = shfl(A, (int)(k0 ? k0 - 1u : 0u));
-        if (k0 == 0u) parent = c.root;
-        bool sc = false;
-        fgk_leader_swap(c, ak, parent, wk, lane, watch, moved, sc);
-        FGK_LEVEL_SYNC();
-        sts32_if(lane == 0, ak, wk + 1u);
-        if (sc) {
-            // an internal node moved: only the entries below the two slots change.  The old slot is
-            // the node of level k0 of this path; ak is now the leader's slot
-            const u32 pf_a = ((k0 + 1u) << 12) | (path >> (depth - 1u - k0));
-            fgk_rebuild_pair(c, pf_a, lds16(c.pfx + ((ak - c.up) >> 2)), lane);
-        }
-        if (parent == c.root) {
-            sts32_if(lane == 0, c.root, count);
-            syncwarp();
-            return;
-        }
-        syncwarp();
-        a = parent;
-        pf = lds16(c.pfx + ((a - c.up) >> 2));            // 2 bytes per slot, 8 bytes per up entry
-    }
+    FgkPre p;
+    p.n = lds64(c.rec + A);
+    p.n1 = lds64(c.rec + A + 8u);
+    p.w2 = lds32(c.rec + A + 16u);
+    p.pfl = lds16(c.pfx + (A >> 2) + 2u);
+    return p;
 }
 
-// fgk_update_plain that also finishes the code of the old path (cursor q) on the way: after the
-// first swap the update continues on another branch of the tree while the code still has to follow
-// the old one.  The two link chases are independent chains, so interleaving them level by level
-// hides the latency of one behind the other.  A further swap (rare) could re-link nodes of the old
-// path, so the chase is completed before any leader search.
-HC_DEV void fgk_update_chase(FgkCtx &c, u32 a, u32 lane, u32 count, u32 q, u32 &hi, u32 &lo, u32 watch, bool &moved, bool &sc)
+// description of the swap of the node with record word y (parent | down << 16) with the leader at
+// offset l (record word yl, pfx pfl).  Branch free on purpose: with an `if (tie)` around it ptxas sinks
+// the loads into the branch and the tied lanes pay a second shared-memory round trip before the REDUX.
+HC_DEV u32 fgk_swap_info(u32 y, u32 yl, u32 l, u32 pfl)
 {
-    const bool w0 = lane == 0;
-    if (a != c.root) {
-        uint2 n = lds64(a);
-        u32 w1 = lds32(a + 8u);
+    u32 info = pfl;
+    info |= ((y ^ l) & 0xffffu) == 0u ? FGK_I_NOSWAP : 0u;               // leader == parent
+    info |= ((y ^ yl) & 0xffffu) == 0u ? FGK_I_SAMEP : 0u;               // same parent
+    info |= ((~(y & yl)) >> 13) & FGK_I_SC;                              // not both leaves (bit 31 of the words)
+    return info;
+}
+static_assert(FGK_I_SC == (0x80000000u >> 13), "bit trick above");
+
+// FGK update of a node whose path is in the table (src/huffman.cpp:113-127).  A = this lane's node
+// (fgk_lookup of pf), pf = depth << 12 | left-aligned path of the node the update starts from.
+// `have`: the caller already did this round's loads (`pre`).
+HC_DEV void fgk_update_rounds(FgkCtx &c, u32 A, u32 pf, u32 lane, bool have, FgkPre pre)
+{
+    const u32 lanebits = (lane << 27) | FGK_I_TIE;
+    u32 guard = 0;
+    for (;;) {
+        if (++guard > 600u) { c.err = 1; return; }       // more rounds than nodes: never on a consistent tree
+        const u32 depth = pf >> 12;
+        if (!have) pre = fgk_preload(c, A);
+        have = false;
+        const u32 W = pre.n.x;
+        const bool tie = lane < depth && pre.n1.x == W;
+        const bool lng = tie && pre.w2 == W;
+        const u32 info = tie ? (lanebits | fgk_swap_info(pre.n.y, pre.n1.y, A + 8u, pre.pfl) | (lng ? FGK_I_LONG : 0u)) : 0u;
+        const u32 ainfo = lng ? ((lane << 27) | A) : 0u;
+        u32 hi = depth;                                   // lanes [0, hi) still have to add 1 to their node
+        bool newpath = false;
         for (;;) {
-            u32 p = n.y;
-            uint2 pn = lds64(p);
-            u32 pw1 = lds32(p + 8u);
-            u32 qn = lds32(q + 4u);                        // unused when q is the root
-            if (w1 == n.x) {
-                for (; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
-                if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved, sc)) {
-                    pn = lds64(p);
-                    pw1 = lds32(p + 8u);
+            u32 r = reduce_max(lane < hi ? info : 0u);
+            const u32 r2 = reduce_max(lane < hi ? ainfo : 0u);
+            syncwarp();                                   // this round's loads precede its stores
+            if (r == 0u) break;
+            const u32 k0 = r >> 27;
+            sts32_if(lane > k0 && lane < hi, c.rec + A, W + 1u);     // plain levels below the tie
+            hi = k0;
+            const bool me = lane == k0;
+            // the swap as the tied lane sees it; replaced by uniform values when the run is long
+            u32 a = A, l = A + 8u, y = pre.n.y, yl = pre.n1.y, w = W;
+            if (r & FGK_I_LONG) {
+                // a run of three or more equal weights: every lane probes one node of the run, then all
+                // lanes fetch the two nodes of the swap (r2 carries the tied node: it is the deepest long tie)
+                a = r2 & 0xffffu;
+                const uint2 na = lds64(c.rec + a);
+                u32 pa = a + 24u + 8u * lane;
+                pa = pa < FGK_SENT_O ? pa : FGK_SENT_O;
+                const u32 m = ~ballot(lds32(c.rec + pa) == na.x);
+                l = m ? a + 8u + 8u * (u32)ffs(m) : fgk_leader(c, a + 24u + 256u, na.x, lane);
+                y = na.y; w = na.x;
+                yl = lds32(c.rec + l + 4u);
+                r = (r & 0xf8000000u) | fgk_swap_info(y, yl, l, lds16(c.pfx + (l >> 2)));
+                syncwarp();                               // these loads precede the tied lane's stores
+            }
+            const u32 pfl = r & 0xffffu;
+            if (me) {
+                if (r & FGK_I_NOSWAP) {
+                    sts32(c.rec + a, w + 1u);
+                } else {
+                    // exchange the contents of a and l (src/huffman.cpp:186-217); the node continues at l.
+                    // Weights here are >= 1, so neither node is the NYT.
+                    const u32 sh = FGK_D - 1u - k0;
+                    const u32 pfa = ((k0 + 1u) << 12) | (((pf & 0x1ffu) >> sh) << sh);
+                    sts16(c.rec + a + 6u, fgk_down(yl));
+                    sts16(c.rec + l + 6u, fgk_down(y));
+                    if (r & FGK_I_SC) {
+                        fgk_relink(c, fgk_down(yl), a, pfa);
+                        fgk_relink(c, fgk_down(y), l, pfl);
+                    } else {
+                        sts32(c.spf + 4u * (fgk_down(yl) & 0xffu), a | (pfa << 16));
+                        sts32(c.spf + 4u * (fgk_down(y) & 0xffu), l | (pfl << 16));
+                    }
+                    sts32(c.rec + l, w + 1u);
                 }
             }
-            if (q != c.root) { fgk_code_bit(q, hi, lo); q = qn; }
-            FGK_LEVEL_SYNC();
-            sts32_if(w0, a, n.x + 1u);
-            if (p == c.root) break;
-            a = p;
-            n = pn;
-            w1 = pw1;
+            if (r & FGK_I_NOSWAP) continue;
+            if (r & FGK_I_SC) {
+                // the old node is level k0 of this path, the leader's path came with r
+                const u32 sh = FGK_D - 1u - k0;
+                c.lev = fgk_rebuild_pair_cold(c, ((k0 + 1u) << 12) | (((pf & 0x1ffu) >> sh) << sh), pfl, lane);
+                c.gen++;
+            } else if (r & FGK_I_SAMEP) {
+                continue;                                 // same parent: the levels above are as loaded
+            }
+            if (pfl == FGK_NOPATH) {
+                // the leader lies deeper than the table: finish sequentially from its parent
+                const u32 pl = shfl(fgk_parent(yl), (int)k0);
+                c = fgk_update_seq(c, pl, lane);
+                c.gen++;
+                return;
+            }
+            if ((pfl >> 12) == 1u) { hi = 0; break; }     // the leader hangs below the root: done
+            pf = pfl - 0x1000u;                           // the parent of the leader: one level up, same path bits
+            A = fgk_lookup(c, pf);
+            newpath = true;
+            break;
         }
+        if (newpath) continue;
+        sts32_if(lane < hi, c.rec + A, W + 1u);
+        syncwarp();
+        return;
     }
-    for (; q != c.root; q = lds32(q + 4u)) fgk_code_bit(q, hi, lo);
-    sts32_if(w0, c.root, count);
-    syncwarp();
 }
 
-// same walk, also collecting the code of the start node in the PRE-update tree
-// (encode precedes update, src/transform.cpp:372-375).  hi:lo must enter as 0x80000000:0.
-// The update path leaves the code path at the first swap; the rest of the old path is then
-// finished by a pure parent chase (safe: the first swap never re-parents an old-path node).
-HC_DEV void fgk_update_coding(FgkCtx &c, u32 a, u32 lane, u32 count, u32 &hi, u32 &lo, u32 watch, bool &moved, bool &sc)
+#if defined(HC_EMU_DEBUG) || defined(HC_FGK_CHECK)
+// debugging aid (emulator debug builds, -DHC_FGK_CHECK device builds): consistency of the whole tree
+// after symbol idx; returns false and prints what is wrong
+HC_DEV bool fgk_validate(const FgkCtx &c, u32 lane, u32 idx)
 {
-    const bool w0 = lane == 0;
-    uint2 n = lds64(a);                       // a is a leaf: never the root
-    u32 w1 = lds32(a + 8u);
-    // two levels per iteration (register sets alternate, see fgk_update_plain)
-    for (;;) {
-        u32 p = n.y;                                       // level A: node a, entry n
-        uint2 pn = lds64(p);
-        u32 pw1 = lds32(p + 8u);
-        fgk_code_bit(a, hi, lo);
-        if (w1 == n.x) {
-            const u32 old_parent = p;
-            if (fgk_leader_swap(c, a, p, n.x, lane, watch, moved, sc)) {
-                FGK_LEVEL_SYNC();
-                sts32_if(w0, a, n.x + 1u);
-                fgk_update_chase(c, p, lane, count, old_parent, hi, lo, watch, moved, sc);
-                return;
-            }
+    if (lane != 0) return true;
+    u32 prevw = 0;
+    bool bad = false;
+    for (u32 o = c.nyt; o < FGK_ROOT_O && !bad; o += 8) {
+        const uint2 r = lds64(c.rec + o);
+        const u32 k = fgk_down(r.y), par = fgk_parent(r.y);
+        const u32 pf = lds16(c.pfx + (o >> 2));
+        if (r.x < prevw) { printf("sym %u: weight order broken at %u\n", idx, o); bad = true; }
+        prevw = r.x;
+        if (par <= o || par > FGK_ROOT_O) { printf("sym %u: parent of %u = %u\n", idx, o, par); bad = true; }
+        else {
+            const u32 pk = fgk_down(lds32(c.rec + par + 4u));
+            if ((pk & FGK_LEAF) || (pk != (o & ~8u))) { printf("sym %u: parent %u of %u has down %x\n", idx, par, o, pk); bad = true; }
         }
-        FGK_LEVEL_SYNC();
-        sts32_if(w0, a, n.x + 1u);
-        if (p == c.root) break;
-        a = pn.y;                                          // level B: node p, entry pn
-        n = lds64(a);
-        w1 = lds32(a + 8u);
-        fgk_code_bit(p, hi, lo);
-        if (pw1 == pn.x) {
-            const u32 old_parent = a;
-            if (fgk_leader_swap(c, p, a, pn.x, lane, watch, moved, sc)) {
-                FGK_LEVEL_SYNC();
-                sts32_if(w0, p, pn.x + 1u);
-                fgk_update_chase(c, a, lane, count, old_parent, hi, lo, watch, moved, sc);
-                return;
-            }
+        if (k & FGK_LEAF) {
+            if (k != FGK_LEAF_NYT) {
+                const u32 sp = lds32(c.spf + 4u * (k & 0xffu));
+                if (sp != (o | (pf << 16))) { printf("sym %u: spf[%u] = %x, leaf at %u pfx %x\n", idx, k & 0xff, sp, o, pf); bad = true; }
+            } else if (o != c.nyt) { printf("sym %u: NYT at %u, c.nyt %u\n", idx, o, c.nyt); bad = true; }
         }
-        FGK_LEVEL_SYNC();
-        sts32_if(w0, p, pn.x + 1u);
-        if (a == c.root) break;
+        if (pf != FGK_NOPATH) {
+            const u32 d = pf >> 12, path = (pf & 0x1ffu) >> (FGK_D - d);
+            const u32 e = lds16(c.pt + 2u * ((1u << d) - 2u + path));
+            if (e != o) { printf("sym %u: pfx[%u] = %x but pt there = %u\n", idx, o, pf, e); bad = true; }
+        }
     }
-    sts32_if(w0, c.root, count);
-    syncwarp();
+    if (bad)
+        for (u32 q = c.nyt; q <= FGK_ROOT_O; q += 8) {
+            const uint2 z = lds64(c.rec + q);
+            printf("   node %u (off %u): w=%u parent=%u down=%x pfx=%x\n", q / 8, q, z.x, fgk_parent(z.y), fgk_down(z.y), lds16(c.pfx + (q >> 2)));
+        }
+    return !bad;
 }
+#endif
 
-// The trees of the resident CTAs no longer hold the whole batch at once, so streams are started in
+// The trees of the resident CTAs do not hold the whole batch at once, so streams are started in
 // order of decreasing length class (counting sort, 4 classes per octave): the long ones first, the
 // short ones fill the slots they free.  One CTA; the order only affects scheduling, never the output.
 HC_DEV u32 fgk_len_class(u64 v)
@@ -532,12 +558,12 @@ fgk_order_kernel(const u64 *HC_RESTRICT len, u32 nf, u32 *HC_RESTRICT order)
         if (fgk_len_class(len[f]) == cls) order[pos++] = f;
 }
 
-// MSB-first bit writer: one 32-bit word per lane, 128-byte coalesced flushes
+// MSB-first bit writer over a 64-word shared-memory ring (c.ring): bits are OR-ed into zeroed words,
+// a half (32 words = 128 bytes) is written out coalesced and zeroed again as soon as the bit position
+// has left it.  Serial puts (lane 0) for long codes and the header, warp-parallel packing for the rest.
 struct BitWriter {
-    u64 acc;
-    u32 nacc;      // valid low bits of acc (< 32 between calls)
-    u32 widx;      // words produced so far
-    u32 mine;      // this lane's word of the current 32-word group
+    u32 pos;       // bit position inside the ring (0..2047)
+    u32 groups;    // 128-byte groups written to `dst`
     u32 *dst;
     u64 cap_words;
     bool overflow;
@@ -545,57 +571,93 @@ struct BitWriter {
 
 HC_DEV void bw_init(BitWriter &b, u8 *dst, u64 cap_bytes)
 {
-    b.acc = 0; b.nacc = 0; b.widx = 0; b.mine = 0;
+    b.pos = 0; b.groups = 0;
     b.dst = (u32 *)dst;
     b.cap_words = cap_bytes / 4;
     b.overflow = false;
 }
 
-HC_DEV void bw_put(BitWriter &b, u32 v, u32 d, u32 lane)   // 0 <= d <= 32, v < 2^d
+// the position moved from `old` to b.pos: write out the half that was left behind
+HC_DEV void bw_advance(const FgkCtx &c, BitWriter &b, u32 old, u32 lane)
 {
-    b.acc = (b.acc << d) | v;
-    b.nacc += d;
-    if (b.nacc >= 32u) {
-        u32 word = (u32)(b.acc >> (b.nacc - 32u));
-        b.nacc -= 32u;
-        if (lane == (b.widx & 31u)) b.mine = bswap32(word);
-        b.widx++;
-        if ((b.widx & 31u) == 0u) {
-            if ((u64)b.widx <= b.cap_words) stg32_stream(b.dst + (b.widx - 32u) + lane, b.mine);
-            else b.overflow = true;
-        }
+    if ((old ^ b.pos) & 1024u) {
+        syncwarp();                                       // all ORs into that half are done
+        const u32 half = c.ring + ((old >> 3) & 128u);
+        const u32 word = lds32(half + 4u * lane);
+        sts32(half + 4u * lane, 0u);
+        if (((u64)b.groups + 1u) * 32u <= b.cap_words) stg32_stream(b.dst + (u64)b.groups * 32u + lane, bswap32(word));
+        else b.overflow = true;
+        b.groups++;
+        syncwarp();
     }
+}
+
+HC_DEV void bw_put(const FgkCtx &c, BitWriter &b, u32 v, u32 d, u32 lane)   // serial: 0 <= d <= 32, v < 2^d
+{
+    if (d == 0u) return;
+    const u32 old = b.pos, off = old & 31u;
+    const u64 bits = ((u64)v << (64u - d)) >> off;        // left aligned at bit `off` of a two-word window
+    syncwarp();
+    if (lane == 0) {
+        const u32 w0 = c.ring + ((old >> 3) & 252u), w1 = c.ring + (((old >> 3) + 4u) & 252u);
+        sts32(w0, lds32(w0) | (u32)(bits >> 32));
+        if ((u32)bits) sts32(w1, lds32(w1) | (u32)bits);
+    }
+    syncwarp();
+    b.pos = (old + d) & 2047u;
+    bw_advance(c, b, old, lane);
 }
 
 // emit the code collected in hi:lo (marker scheme of fgk_code_bit); returns false if the code is
 // longer than 56 bits (impossible below 2^32 symbols)
-HC_DEV bool bw_put_code(BitWriter &b, u32 hi, u32 lo, u32 lane)
+HC_DEV bool bw_put_code(const FgkCtx &c, BitWriter &b, u32 hi, u32 lo, u32 lane)
 {
     if (lo == 0u) {                                   // depth <= 31: everything is in hi
         const u32 d = 32u - (u32)ffs(hi);             // marker = lowest set bit of hi
-        if (d) bw_put(b, hi >> (32u - d), d, lane);
+        bw_put(c, b, d ? hi >> (32u - d) : 0u, d, lane);
         return true;
     }
     const u32 d2 = 32u - (u32)ffs(lo);                // bits of the code that live in lo
-    bw_put(b, hi, 32, lane);
-    if (d2) bw_put(b, lo >> (32u - d2), d2, lane);
+    bw_put(c, b, hi, 32, lane);
+    bw_put(c, b, d2 ? lo >> (32u - d2) : 0u, d2, lane);
     return d2 <= 24u;
 }
 
-// flush the tail; returns the total number of bytes of the stream
-HC_DEV u64 bw_finish(BitWriter &b, u32 lane)
+// warp-parallel: lane j contributes the table code parked in `code` (pfx format, 0 = nothing), in lane order
+HC_DEV void bw_pack(const FgkCtx &c, BitWriter &b, u32 code, u32 lane)
 {
-    u32 rem = b.widx & 31u;
-    u32 base = b.widx - rem;
-    u32 tail_bytes = (b.nacc + 7u) / 8u;
-    u64 total = (u64)b.widx * 4u + tail_bytes;
-    if (total > b.cap_words * 4u) { b.overflow = true; return total; }
-    if (lane < rem) b.dst[base + lane] = b.mine;
-    if (lane == 0 && tail_bytes) {
-        u32 word = (u32)(b.acc << (32u - b.nacc));           // left-align, zero padded
-        u8 *p = (u8 *)(b.dst + b.widx);
-        for (u32 i = 0; i < tail_bytes; i++) p[i] = (u8)(word >> (24u - 8u * i));
+    const u32 d = code >> 12;
+    u32 inc = d;                                          // inclusive scan of the lengths (<= 9 * 32)
+#pragma unroll
+    for (u32 s = 1; s < 32u; s <<= 1) {
+        const u32 x = shfl_up(inc, s);
+        if (lane >= s) inc += x;
     }
+    const u32 total = shfl(inc, 31);
+    if (total == 0u) return;
+    const u32 old = b.pos, p = old + inc - d, off = p & 31u;
+    if (d) {
+        const u64 bits = ((u64)((code & 0x1ffu) >> (FGK_D - d)) << (64u - d)) >> off;
+        atomic_or_smem(c.ring + ((p >> 3) & 252u), (u32)(bits >> 32));
+        if ((u32)bits) atomic_or_smem(c.ring + (((p >> 3) + 4u) & 252u), (u32)bits);
+    }
+    b.pos = (old + total) & 2047u;
+    bw_advance(c, b, old, lane);
+}
+
+// flush the tail; returns the total number of bytes of the stream
+HC_DEV u64 bw_finish(const FgkCtx &c, BitWriter &b, u32 lane)
+{
+    syncwarp();
+    const u32 in_half = b.pos & 1023u;                    // bits pending in the current half
+    const u32 nbytes = (in_half + 7u) / 8u;
+    const u64 total = (u64)b.groups * 128u + nbytes;
+    if (total > b.cap_words * 4u) { b.overflow = true; return total; }
+    const u32 half = c.ring + ((b.pos >> 3) & 128u);
+    const u32 word = bswap32(lds32(half + 4u * lane));    // big-endian word -> bytes in stream order
+    u8 *p = (u8 *)(b.dst + (u64)b.groups * 32u + lane);
+    if (4u * lane + 4u <= nbytes) *(u32 *)p = word;
+    else for (u32 i = 0; 4u * lane + i < nbytes; i++) p[i] = (u8)(word >> (8u * i));
     return total;
 }
 
@@ -614,81 +676,110 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
     FgkCtx c;
     fgk_init(c, trees[wid], lane);
 
-    const u64 m = sym_len[f];
+    const u64 m64 = sym_len[f];
+    const bool too_many = m64 > 0xfffffff0ull;            // weights are 32-bit
+    const u32 m = too_many ? 0u : (u32)m64;
     const u32 *src = (const u32 *)(sym + sym_off[f]);     // 256-byte aligned region
     BitWriter bw;
     bw_init(bw, out + out_off[f], out_cap[f] & ~(u64)3);
     // container header <u64 LE count><u8 flags> (src/headers.cpp:107-125) through the bit writer
-    bw_put(bw, bswap32((u32)m), 32, lane);
-    bw_put(bw, bswap32((u32)(m >> 32)), 32, lane);
-    bw_put(bw, flags ? flags[f] : 0u, 8, lane);
+    bw_put(c, bw, bswap32((u32)m64), 32, lane);
+    bw_put(c, bw, bswap32((u32)(m64 >> 32)), 32, lane);
+    bw_put(c, bw, flags ? flags[f] : 0u, 8, lane);
 
-    bool too_long = m > 0xfffffff0ull;                    // weights are 32-bit
-    u32 chunk = 0;                                        // 4 symbols per lane, 128 per warp
-    if (m > 0) chunk = ldg32(src + lane);
-    u32 count = 0;
-    for (u64 i0 = 0; i0 < m; i0 += 128) {
-        syncwarp();                                       // every lane is done with the previous buffer
-        sts32(c.buf + 4u * lane, chunk);
+    bool too_long = too_many;
+    // symbols are staged 128 at a time (4 per lane) in a two-half ring, one chunk ahead, so that the
+    // lookups of the next symbol can run ahead of the update across chunk boundaries
+    u32 cnext = 0;
+    if (m > 0) sts32(c.buf + 4u * lane, ldg32(src + lane));
+    if (m > 128) cnext = ldg32(src + 32 + lane);
+    syncwarp();
+    // software pipeline: symbol -> spf (leaf, code) -> per-lane nodes of its path (A), one symbol ahead
+    u32 y0 = lds8(c.buf), y1 = lds8(c.buf + 1u);
+    u32 sp0 = lds32(c.spf + 4u * y0);
+    u32 A0 = fgk_lookup(c, sp0 >> 16);
+    u32 gen0 = c.gen;                                     // table generation A0 was looked up in
+    u32 code = 0;                                         // this lane's parked table code
+    for (u32 i0 = 0; i0 < m; i0 += 128) {
+        syncwarp();                                       // every lane is done with the half that is overwritten
+        sts32(c.buf + ((i0 + 128u) & 128u) + 4u * lane, cnext);
         syncwarp();
-        if (i0 + 128 < m) chunk = ldg32(src + (i0 + 128) / 4 + lane);   // prefetch the next 128 symbols
-        const u32 cnt = (m - i0) < 128 ? (u32)(m - i0) : 128u;
-        u32 y = lds8(c.buf);
-        u32 slot = lds16(c.slot_of + 2u * y);
+        if (i0 + 256u < m) cnext = ldg32(src + (i0 + 256u) / 4u + lane);   // prefetch the chunk after the next
+        const u32 cnt = (m - i0) < 128u ? (m - i0) : 128u;
         for (u32 i = 0; i < cnt; i++) {
-            // fetch the next symbol and its leaf slot before the update; the update reports if
-            // that leaf moved (swap) or was created (same new symbol twice) so the slot is re-read
-            const u32 yn = lds8(c.buf + ((i + 1u) & 127u));
-            u32 slot_n = lds16(c.slot_of + 2u * yn);
-            bool moved = false;
-            count++;
-            if (slot == 0xffffu) {
-                // not yet transmitted: NYT code followed by the 8 raw bits (src/huffman.cpp:42-51)
-                u32 hi = 0x80000000u, lo = 0u;
-                for (u32 p = c.nyt; p != c.root; p = lds32(p + 4u)) fgk_code_bit(p, hi, lo);
-                if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
-                bw_put(bw, y, 8, lane);
-                const u32 nsl = c.nyt, npf = nsl == c.root ? 0u : lds16(c.pfx + ((nsl - c.up) >> 2));
-                const u32 leaf = fgk_split(c, y, lane);
-                fgk_table_split(c, nsl, npf, lane);
-                c = fgk_update_plain_cold(c, leaf, lane, count, yn);
-                if (c.fl & 1u) moved = true;
-                if (yn == y) moved = true;
-            } else {
-                const u32 pf = lds16(c.pfx + 2u * slot);
-                if (pf != FGK_NOPATH) {
-                    // the code of a leaf is its path (encode precedes update, src/transform.cpp:372-375)
-                    bw_put(bw, pf & 0xfffu, pf >> 12, lane);
-                    fgk_update_fast(c, c.up + 8u * slot, pf, lane, count, yn, moved);
-                } else {
-                    u32 hi = 0x80000000u, lo = 0u;
-                    bool sc = false;
-                    fgk_update_coding(c, c.up + 8u * slot, lane, count, hi, lo, yn, moved, sc);
-                    if (sc) fgk_rebuild(c, lane);
-                    if (!bw_put_code(bw, hi, lo, lane)) too_long = true;
-                }
+            // The entry of this symbol was fetched one symbol ago, before the previous update: re-read it (a
+            // leaf that moved shows up as a different word) and compare the table generation (two subtree
+            // swaps in one update can bring a leaf back to the same path through different nodes).  The next
+            // symbol's lookups are issued before this symbol's update.
+            const u32 chk = lds32(c.spf + 4u * y0);
+            const u32 sp1 = lds32(c.spf + 4u * y1);
+            const u32 y2 = lds8(c.buf + ((i0 + i + 2u) & 255u));
+            FgkPre pre = fgk_preload(c, A0);
+            const u32 A1 = fgk_lookup(c, sp1 >> 16);
+            const u32 gen1 = c.gen;
+            bool have = true;
+            if (chk != sp0 || gen0 != gen1) {
+                sp0 = chk;
+                A0 = fgk_lookup(c, sp0 >> 16);
+                have = false;
             }
-            if (moved) slot_n = lds16(c.slot_of + 2u * yn);
-            y = yn;
-            slot = slot_n;
+            const u32 pf0 = sp0 >> 16;
+            if (pf0 == FGK_NOPATH) {
+                // Not yet transmitted, or deeper than the table.  Encode precedes update (src/transform.cpp:372-375):
+                // the code is read off the tree first, by a parent chase; a new symbol sends the NYT code + 8 raw
+                // bits (src/huffman.cpp:42-51), then splits.
+                bw_pack(c, bw, code, lane);
+                code = 0;
+                const bool isnew = sp0 == FGK_SPF_NONE;
+                u32 hi = 0x80000000u, lo = 0u, start = sp0 & 0xffffu;
+                fgk_code_of(c, isnew ? c.nyt : start, hi, lo);
+                if (!bw_put_code(c, bw, hi, lo, lane)) too_long = true;
+                if (isnew) {
+                    bw_put(c, bw, y0, 8, lane);
+                    const u32 n = c.nyt, pn = n == FGK_ROOT_O ? 0u : lds16(c.pfx + (n >> 2));
+                    start = fgk_split(c, y0, lane);
+                    fgk_table_split(c, n, pn, lane);
+                }
+                c = fgk_update_seq(c, start, lane);
+            } else {
+                // the code of a leaf is its path (encode precedes update, src/transform.cpp:372-375)
+                if (lane == ((i0 + i) & 31u)) code = pf0;
+                fgk_update_rounds(c, A0, pf0, lane, have, pre);
+            }
+            if (((i0 + i) & 31u) == 31u) {
+                bw_pack(c, bw, code, lane);
+                code = 0;
+            }
+#if defined(HC_EMU_DEBUG) || defined(HC_FGK_CHECK)
+            syncwarp();
+            if (!c.err && ballot(!fgk_validate(c, lane, i0 + i))) { c.err = 2; }
+            syncwarp();
+            if (c.err) { i0 = m; break; }
+#endif
+            y0 = y1; y1 = y2;
+            sp0 = sp1;
+            A0 = A1;
+            gen0 = gen1;
         }
     }
-    u64 total = bw_finish(bw, lane);
+    bw_pack(c, bw, code, lane);
+    u64 total = bw_finish(c, bw, lane);
     if (lane == 0) {
         out_len[f] = total;
-        status[f] = too_long ? 101 : (bw.overflow ? 100 : 0);
+        status[f] = c.err ? 102 : (too_long ? 101 : (bw.overflow ? 100 : 0));
     }
 }
 
-// MSB-first bit reader over 128-byte chunks held one word per lane
+// MSB-first bit reader over 128-byte chunks held one word per lane.  Reading past the end yields
+// zeros; the caller compares br_consumed with the length at the end (a truncated stream decodes
+// garbage that is then discarded with status 9).
 struct BitReader {
     u64 win;        // next bits, MSB aligned
     u32 wbits;      // valid bits in win (> 32 between calls)
     u32 ridx;       // next word index to pull into the window
     u32 chunk, chunk_next;
     const u32 *src;
-    u64 nwords;     // words that may be loaded
-    u64 avail;      // bits of the file not yet consumed
+    u32 nwords;     // words that may be loaded
 };
 
 HC_DEV void br_refill(BitReader &r, u32 lane)
@@ -700,7 +791,7 @@ HC_DEV void br_refill(BitReader &r, u32 lane)
     r.ridx++;
     if ((r.ridx & 31u) == 0u) {
         r.chunk = r.chunk_next;
-        u64 nx = (u64)r.ridx + 32u + lane;
+        const u32 nx = r.ridx + 32u + lane;
         r.chunk_next = nx < r.nwords ? ldg32(r.src + nx) : 0u;
     }
 }
@@ -708,8 +799,7 @@ HC_DEV void br_refill(BitReader &r, u32 lane)
 HC_DEV void br_init(BitReader &r, const u8 *p, u64 len_bytes, u32 lane)
 {
     r.src = (const u32 *)p;
-    r.nwords = (len_bytes + 3u) / 4u;      // reads stay inside the padded region
-    r.avail = len_bytes * 8u;
+    r.nwords = (u32)((len_bytes + 3u) / 4u);      // reads stay inside the padded region
     r.chunk = lane < r.nwords ? ldg32(r.src + lane) : 0u;
     r.chunk_next = 32u + lane < r.nwords ? ldg32(r.src + 32u + lane) : 0u;
     r.win = 0; r.wbits = 0; r.ridx = 0;
@@ -722,15 +812,54 @@ HC_DEV void br_skip(BitReader &r, u32 d, u32 lane)
 {
     r.win <<= d;
     r.wbits -= d;
-    r.avail -= d;
     if (r.wbits <= 32u) br_refill(r, lane);
 }
 
-HC_DEV u32 br_get(BitReader &r, u32 d, u32 lane)   // 1..32 bits; caller checks r.avail first
+HC_DEV u32 br_get(BitReader &r, u32 d, u32 lane)   // 1..32 bits
 {
     u32 v = (u32)(r.win >> (64u - d));
     br_skip(r, d, lane);
     return v;
+}
+
+HC_DEV u64 br_consumed(const BitReader &r) { return (u64)r.ridx * 32u - r.wbits; }
+
+// cold half of the decoder (src/huffman.cpp:60-93): the root is still a leaf, the code is longer
+// than the path table, or the symbol arrives raw behind the NYT code.  Walks down bit by bit (codes
+// beyond 32 bits included), then updates sequentially.
+HC_DEV u32 fgk_decode_cold(FgkCtx &c, BitReader &br, u32 lane)
+{
+    u32 d = FGK_ROOT_O, k = fgk_down(lds32(c.rec + d + 4u)), len = 0;
+    u32 t = (u32)(br.win >> 32), guard = 0;
+    while (!(k & FGK_LEAF)) {
+        if (++guard > 600u || k >= FGK_ROOT_O) { c.err = 1; return 0; }
+        if (len == 32u) {
+            br_skip(br, 32, lane);
+            t = (u32)(br.win >> 32);
+            len = 0;
+        }
+        d = k + ((t >> 28) & 8u);
+        t <<= 1;
+        len++;
+        k = fgk_down(lds32(c.rec + d + 4u));
+    }
+    if (len) br_skip(br, len, lane);
+    if (k != FGK_LEAF_NYT) {
+        c = fgk_update_seq(c, d, lane);
+        return k & 0xffu;
+    }
+    const u32 y = br_get(br, 8, lane);
+    // a raw symbol that is already in the tree is still decoded as that symbol
+    // (src/huffman.cpp:74-86); the update then starts from its existing leaf
+    const u32 sp = lds32(c.spf + 4u * y);
+    u32 start = sp & 0xffffu;
+    if (sp == FGK_SPF_NONE) {
+        const u32 n = c.nyt, pn = n == FGK_ROOT_O ? 0u : lds16(c.pfx + (n >> 2));
+        start = fgk_split(c, y, lane);
+        fgk_table_split(c, n, pn, lane);
+    }
+    c = fgk_update_seq(c, start, lane);
+    return y;
 }
 
 HC_KERNEL HC_LAUNCH_BOUNDS(FGK_DEC_WARPS * 32, 1)
@@ -757,135 +886,62 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     br_init(br, in + in_off[f], n, lane);
     u32 lo = bswap32(br_get(br, 32, lane));
     u32 hi = bswap32(br_get(br, 32, lane));
-    const u64 m = ((u64)hi << 32) | lo;
+    const u64 m64 = ((u64)hi << 32) | lo;
     u32 fl = br_get(br, 8, lane);
     if (lane == 0 && flags) flags[f] = (u8)fl;
-    const u64 cap = sym_cap[f];
-    if (m > cap || m > br.avail + 1u || m > 0xfffffff0ull) {
+    const u64 cap = sym_cap[f], avail = n * 8u - 72u;
+    if (m64 > cap || m64 > avail + 1u || m64 > 0xfffffff0ull) {
         // every symbol after the first costs >= 1 bit: a count beyond avail+1 is a guaranteed
         // underrun, for which the reference exits with 9 (src/transform.cpp:394-398)
-        if (lane == 0) { sym_len[f] = m; status[f] = (m > br.avail + 1u) ? 9 : 100; }
+        if (lane == 0) { sym_len[f] = m64; status[f] = (m64 > avail + 1u) ? 9 : 100; }
         return;
     }
+    const u32 m = (u32)m64;
     u32 *dst = (u32 *)(sym + sym_off[f]);
-    const u32 root_down = c.down + 4u * FGK_ROOT;
-    i32 err = 0;
-    u32 count = 0;
-    for (u64 i = 0; i < m; i++) {
+    const u32 shd = 31u - (lane < FGK_D ? lane : 0u);
+    const u32 lanekey = lane << 16;
+    u32 e = 0;
+    bool have_e = false;
+    for (u32 i = 0; i < m; i++) {
         // The path table resolves the next FGK_D code bits in one step: lane j looks up the node that
-        // the first j + 1 bits lead to; the shallowest leaf among them ends the code.
-        u32 t = (u32)(br.win >> 32), depth = 0, k = 0, d = 0, dk = 0, aleaf = 0;
-        u32 e = 0, kj = 0;
-        if (lane < FGK_D) e = lds16(c.pt + 2u * ((2u << lane) - 2u + (t >> (31u - lane))));
-        if (e) kj = lds32(c.down + 4u * (e - 1u));
-        // the update's first question ("does a level need a leader search?") rides on the same round
-        // of loads: weights of the node and of the slot after it (no node: the root, which never ties)
-        const u32 A1 = e ? c.up - 8u + 8u * e : c.root;
-        const u32 W1 = lds32(A1), W1n = lds32(A1 + 8u);
-        const u32 leafm = ballot(e != 0u && (kj & 1u));
-        const bool via_table = leafm != 0u;
-        if (via_table) {
-            depth = (u32)ffs(leafm);
-            k = shfl(kj, (int)(depth - 1u));
-            aleaf = c.up - 8u + 8u * shfl(e, (int)(depth - 1u));
-            if (br.avail < depth) { err = 9; break; }    // ran out of bits inside a code
-        } else {
-            // the root is still a leaf, or the code is longer than the table: walk down on a private
-            // copy of the window's top 32 bits, consume them afterwards.  Lane j remembers the node
-            // reached after j+1 steps.  No length check inside the loop: past 32 steps `t` only supplies
-            // zeros, i.e. the walk keeps taking (valid) left children and still ends at a leaf; such a
-            // symbol is redone below.
-            d = root_down; k = lds32(d);
-            while (!(k & 1u)) {
-                d = k + ((t >> 29) & 4u);
-                if (lane == depth) dk = d;
-                t <<= 1;
-                depth++;
-                k = lds32(d);
-            }
-            if (depth > 32u) {
-                // code longer than 32 bits (very deep tree): exact walk, 32 bits at a time
-                d = root_down; k = lds32(d); t = (u32)(br.win >> 32); depth = 0;
-                u32 len = 0;
-                while (!(k & 1u)) {
-                    if (len == 32u) {
-                        if (br.avail < 32u) { err = 9; break; }
-                        br_skip(br, 32, lane);
-                        t = (u32)(br.win >> 32);
-                        len = 0;
-                    }
-                    d = k + ((t >> 29) & 4u);
-                    t <<= 1;
-                    len++;
-                    depth++;
-                    k = lds32(d);
-                }
-                if (err) break;
-                if (len) {
-                    if (br.avail < len) { err = 9; break; }
-                    br_skip(br, len, lane);
-                }
-            } else if (depth) {
-                if (br.avail < depth) { err = 9; break; }
-            }
-        }
-        const u32 pf_leaf = (depth << 12) | (t >> ((32u - depth) & 31u));   // used on the table path only (t intact, depth >= 1)
-        if (depth && depth <= 32u) br_skip(br, depth, lane);
-        count++;
+        // the first j + 1 bits lead to; the shallowest leaf among them ends the code (REDUX.MIN over
+        // lane << 16 | symbol).  The loads of the update's first round ride on the same round of loads.
+        const u32 t = (u32)(br.win >> 32);
+        if (!have_e) e = lane < FGK_D ? lds16(c.ptj + 2u * (t >> shd)) : FGK_ROOT_O;
+        have_e = false;
+        const FgkPre pre = fgk_preload(c, e);
+        const u32 ka = fgk_down(pre.n.y);
+        const u32 r = reduce_min((e != FGK_ROOT_O && (ka & FGK_LEAF)) ? (lanekey | (ka & 0x1ffu)) : 0xffffffffu);
         u32 y;
-        bool moved = false, sc = false;
-        if (k == FGK_LEAF_NYT) {
-            if (br.avail < 8u) { err = 9; break; }
-            y = br_get(br, 8, lane);
-            // a raw symbol that is already in the tree is still decoded as that symbol
-            // (src/huffman.cpp:74-86); the update then starts from its existing leaf
-            const u32 ex = lds16(c.slot_of + 2u * y);
-            if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
-            if (ex == 0xffffu) {
-                const u32 nsl = c.nyt, npf = nsl == c.root ? 0u : lds16(c.pfx + ((nsl - c.up) >> 2));
-                const u32 a = fgk_split(c, y, lane);
-                fgk_table_split(c, nsl, npf, lane);
-                c = fgk_update_plain_cold(c, a, lane, count, 0x1ffu);     // ends with a warp barrier
-            } else {
-                fgk_update_fast(c, c.up + 8u * ex, lds16(c.pfx + 2u * ex), lane, count, 0x1ffu, moved);
-            }
+        if (r == 0xffffffffu || (r & 0x100u)) {
+            y = fgk_decode_cold(c, br, lane);
         } else {
-            y = k >> 1;
-            if (lane == 0) sts8(c.buf + (u32)(i & 127u), y);
-            if (via_table) {
-                fgk_update_fast(c, aleaf, pf_leaf, lane, count, 0x1ffu, moved, true, A1, W1, W1n);
-            } else if (depth <= 32u) {
-                // all levels at once, one lane per level (lane depth-1 = the leaf): a level whose next
-                // slot carries the same weight needs leader search / swap and everything above it may
-                // move, so the sequential walk takes over from the deepest such level.
-                const bool valid = lane < depth;
-                const u32 A = valid ? fgk_up_of(c, dk) : c.sentinel - 8u;
-                const u32 W = lds32(A), w1 = lds32(A + 8u);
-                const u32 tm = ballot(valid && w1 == W);
-                FGK_LEVEL_SYNC();
-                if (tm == 0u) {
-                    sts32_if(valid, A, W + 1u);
-                    sts32_if(lane == 0, c.root, count);
-                    syncwarp();
-                } else {
-                    const u32 k0 = 31u - (u32)clz(tm);                   // deepest level with a tie
-                    sts32_if(valid && lane > k0, A, W + 1u);             // plain levels below it
-                    c = fgk_update_plain_cold(c, shfl(A, (int)k0), lane, count, 0x1ffu);
-                }
-            } else {
-                c = fgk_update_plain_cold(c, fgk_up_of(c, d), lane, count, 0x1ffu);
-            }
+            const u32 depth = (r >> 16) + 1u;
+            y = r & 0xffu;
+            br_skip(br, depth, lane);
+            // the next code starts here: its table lookup does not depend on this symbol's update
+            // unless the tree changes shape (c.gen moves)
+            const u32 t2 = (u32)(br.win >> 32);
+            const u32 e2 = lane < FGK_D ? lds16(c.ptj + 2u * (t2 >> shd)) : FGK_ROOT_O;
+            const u32 gen = c.gen;
+            fgk_update_rounds(c, e, (depth << 12) | (t >> 23), lane, true, pre);
+            e = e2;
+            have_e = gen == c.gen;
         }
+        if (lane == 0) sts8(c.buf + (i & 127u), y);
         if ((i & 127u) == 127u) {
+            syncwarp();
             stg32_stream(dst + (i >> 7) * 32u + lane, lds32(c.buf + 4u * lane));
             syncwarp();
         }
     }
-    if (!err) {
-        u32 rem = (u32)(m & 127u);                         // symbols in the last partial group
+    const bool underrun = br_consumed(br) > n * 8u;
+    if (!underrun) {
+        u32 rem = m & 127u;                                // symbols in the last partial group
+        syncwarp();
         if (rem && lane < (rem + 3u) / 4u) dst[(m >> 7) * 32u + lane] = lds32(c.buf + 4u * lane);
     }
-    if (lane == 0) { sym_len[f] = m; status[f] = err; }
+    if (lane == 0) { sym_len[f] = m64; status[f] = c.err ? 102 : (underrun ? 9 : 0); }
 }
 
 }  // namespace hcd

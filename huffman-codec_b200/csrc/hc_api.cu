@@ -3,7 +3,7 @@
 //
 // Product build: nvcc -gencode arch=compute_100a,code=sm_100a -> libhc_b200.so.  There is no CPU
 // implementation behind these entry points.  (-DHC_EMU builds the SIMT-emulated test double used
-// by tests/emu only; see hc_emu.h.)
+// by tests/emu only; see tests/emu/hc_emu.h.)
 #include "../../include/hc_b200.h"
 
 #include <atomic>
@@ -169,7 +169,11 @@ static inline dim3 grid2(u64 x, u32 nf)
 using namespace hcd;
 
 // ======================================================================= misc
-extern "C" const char *hc_version(void) { return "hc_b200 0.1 (sm_100a)"; }
+#ifdef HC_EMU
+extern "C" const char *hc_version(void) { return "hc_b200 0.2 (SIMT emulator, tests only)"; }
+#else
+extern "C" const char *hc_version(void) { return "hc_b200 0.2 (sm_100a)"; }
+#endif
 
 extern "C" int hc_device_count(void)
 {
@@ -195,6 +199,7 @@ extern "C" const char *hc_error_string(int code)
     case 15: return "leftover data of adaptive block RLE detected";
     case 100: return "output capacity too small";
     case 101: return "FGK code longer than 56 bits";
+    case 102: return "internal error: inconsistent FGK tree";
     default: return "unknown";
     }
 }
@@ -331,11 +336,8 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
     // matrices up to 512 x 512: search from equality bitmasks in shared memory (adapt_mask.cuh);
     // larger ones: generic per-block evaluation
 #ifndef HC_EMU
-    static bool smem_attr_set = false;
-    if (!smem_attr_set) {
-        HC_CUDA(cudaFuncSetAttribute(adapt_cost_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACM_SMEM));
-        smem_attr_set = true;
-    }
+    // per device and per context: set on every call (cheap) rather than once per process
+    HC_CUDA(cudaFuncSetAttribute(adapt_cost_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACM_SMEM));
 #endif
     HC_LAUNCH(adapt_cost_mask_kernel, dim3(nf < 1184u ? nf : 1184u), dim3(ACM_TPB), ACM_SMEM, stream, in, in_off, width, height,
               nf, cost, cs);
@@ -368,11 +370,7 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
     }
     // files whose winning block size is 8/16/32: one thread per block over shared-memory staged rows
 #ifndef HC_EMU
-    static bool emit_attr_set = false;
-    if (!emit_attr_set) {
-        HC_CUDA(cudaFuncSetAttribute(adapt_emit_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADS_SMEM));
-        emit_attr_set = true;
-    }
+    HC_CUDA(cudaFuncSetAttribute(adapt_emit_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADS_SMEM));
 #endif
     {
         u64 gx = max_len / ADS_STRIP + 1;
@@ -437,11 +435,7 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
         HC_CHECK_LAUNCH();
     }
 #ifndef HC_EMU
-    static bool exp_attr_set = false;
-    if (!exp_attr_set) {
-        HC_CUDA(cudaFuncSetAttribute(adapt_expand_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADS_SMEM));
-        exp_attr_set = true;
-    }
+    HC_CUDA(cudaFuncSetAttribute(adapt_expand_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADS_SMEM));
 #endif
     {
         u64 gx = max_out_len / ADS_STRIP + 1;
@@ -1021,6 +1015,8 @@ extern "C" int hc_decompress_batch(hc_codec *c,
     }
     // phase 2: in file order: offsets of the group, expansion straight into a compact buffer, copy out
     u64 total = 0;
+    std::vector<u8> oversize(nf, 0);
+    std::vector<u64> need(nf, 0);
     for (u32 g = 0; g < ng; g++) {
         hc_codec *k = c->kids[g];
         GroupJob &j = jobs[g];
@@ -1031,20 +1027,20 @@ extern "C" int hc_decompress_batch(hc_codec *c,
         u64 *h = (u64 *)k->htab.p;
         memcpy(out_len + j.lo, h + 4 * N, N * 8);
         memcpy(status + j.lo, h + 5 * N, N * 4);
+        memcpy(need.data() + j.lo, h + 4 * N, N * 8);
         const u64 start = total;
         u64 max_out = 0;
         for (u32 i = 0; i < n; i++) {
             const u32 f = j.lo + i;
-            const u64 len = status[f] == 0 ? out_len[f] : 0;
+            u64 len = status[f] == 0 ? out_len[f] : 0;
+            // a file that does not fit any more fails alone (HC_E_CAPACITY, out_len = the size it needs); the
+            // other files of the batch are not affected
+            if (total + align_up(len, 16) > out_cap_total || total + align_up(len, 16) < total) { oversize[f] = 1; len = 0; }
             out_off[f] = total;
             h[2 * N + i] = total - start;
             h[3 * N + i] = align_up(len, 16);
             if (len > max_out) max_out = len;
             total += align_up(len, 16);
-        }
-        if (total > out_cap_total) {
-            for (u32 q = 0; q < ng; q++) cudaStreamSynchronize(c->kids[q]->stream);
-            return HC_E_CAPACITY;
         }
         const u64 gbytes = total - start;
         HC_TRY(k->out.ensure((size_t)gbytes + 512));
@@ -1062,7 +1058,9 @@ extern "C" int hc_decompress_batch(hc_codec *c,
         memcpy(out_len + jobs[g].lo, h + 4 * N, N * 8);
         memcpy(status + jobs[g].lo, h + 5 * N, N * 4);
     }
-    for (u32 i = 0; i < nf; i++)
-        if (status[i] != 0) out_len[i] = 0;
+    for (u32 i = 0; i < nf; i++) {
+        if (oversize[i]) { status[i] = HC_E_CAPACITY; out_len[i] = need[i]; }
+        else if (status[i] != 0) out_len[i] = 0;
+    }
     return 0;
 }

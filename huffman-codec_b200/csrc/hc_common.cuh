@@ -1,7 +1,8 @@
 // hc_common.cuh -- shared device helpers for the sm_100a kernels of libhc_b200.
 //
 // Product build: nvcc -gencode arch=compute_100a,code=sm_100a.  Every helper maps 1:1 to a
-// CUDA intrinsic.  The -DHC_EMU branch exists only for tests/emu (see hc_emu.h).
+// CUDA intrinsic.  The -DHC_EMU branch exists only for the test double built by tests/backend.py
+// (tests/emu/hc_emu.h, found through that build's -I tests/emu; the product build never sees it).
 #pragma once
 
 #include <stddef.h>
@@ -58,26 +59,33 @@ constexpr u32 FULL = 0xffffffffu;
 
 #ifdef HC_EMU
 // ---------------------------------------------------------------- emulation
+#ifdef HC_EMU_DEBUG
+#define HC_SITE , __builtin_return_address(0)
+#undef HC_DEV
+#define HC_DEV static __attribute__((noinline))
+#else
+#define HC_SITE
+#endif
 HC_DEV void syncthreads() { hc_emu::syncthreads(); }
-HC_DEV void syncwarp() { hc_emu::warp_exchange(0); }
+HC_DEV void syncwarp() { hc_emu::warp_exchange(0 HC_SITE); }
 HC_DEV u32 lane_id() { return threadIdx.x & 31u; }
-HC_DEV u64 shfl64(u64 v, int src) { return hc_emu::warp_exchange(v)[src & 31]; }
+HC_DEV u64 shfl64(u64 v, int src) { return hc_emu::warp_exchange(v HC_SITE)[src & 31]; }
 HC_DEV u64 shfl_up64(u64 v, unsigned d)
 {
     unsigned l = hc_emu::lane();
-    const u64 *s = hc_emu::warp_exchange(v);
+    const u64 *s = hc_emu::warp_exchange(v HC_SITE);
     return l >= d ? s[l - d] : v;
 }
 HC_DEV u64 shfl_down64(u64 v, unsigned d)
 {
     unsigned l = hc_emu::lane();
-    const u64 *s = hc_emu::warp_exchange(v);
+    const u64 *s = hc_emu::warp_exchange(v HC_SITE);
     return l + d < 32 ? s[l + d] : v;
 }
 HC_DEV u64 shfl_xor64(u64 v, unsigned m)
 {
     unsigned l = hc_emu::lane();
-    return hc_emu::warp_exchange(v)[l ^ m];
+    return hc_emu::warp_exchange(v HC_SITE)[l ^ m];
 }
 HC_DEV u32 shfl(u32 v, int src) { return (u32)shfl64(v, src); }
 HC_DEV u32 shfl_up(u32 v, unsigned d) { return (u32)shfl_up64(v, d); }
@@ -85,10 +93,26 @@ HC_DEV u32 shfl_down(u32 v, unsigned d) { return (u32)shfl_down64(v, d); }
 HC_DEV u32 shfl_xor(u32 v, unsigned m) { return (u32)shfl_xor64(v, m); }
 HC_DEV u32 ballot(bool p)
 {
-    const u64 *s = hc_emu::warp_exchange(p ? 1 : 0);
+    const u64 *s = hc_emu::warp_exchange(p ? 1 : 0 HC_SITE);
     u32 live = hc_emu::warp_live(), r = 0;
     for (int i = 0; i < 32; i++)
         if (((live >> i) & 1) && s[i]) r |= 1u << i;
+    return r;
+}
+HC_DEV u32 reduce_max(u32 v)
+{
+    const u64 *s = hc_emu::warp_exchange(v HC_SITE);
+    u32 live = hc_emu::warp_live(), r = 0;
+    for (int i = 0; i < 32; i++)
+        if (((live >> i) & 1) && (u32)s[i] > r) r = (u32)s[i];
+    return r;
+}
+HC_DEV u32 reduce_min(u32 v)
+{
+    const u64 *s = hc_emu::warp_exchange(v HC_SITE);
+    u32 live = hc_emu::warp_live(), r = 0xffffffffu;
+    for (int i = 0; i < 32; i++)
+        if (((live >> i) & 1) && (u32)s[i] < r) r = (u32)s[i];
     return r;
 }
 HC_DEV int popc(u32 v) { return __builtin_popcount(v); }
@@ -151,6 +175,7 @@ HC_DEV void sts16(u32 a, u32 v) { u16 t = (u16)v; memcpy(g_emu_smem_base + a, &t
 HC_DEV void sts8(u32 a, u32 v) { g_emu_smem_base[a] = (u8)v; }
 HC_DEV u32 funnel_r(u32 lo, u32 hi, u32 sh) { return (u32)((((u64)hi << 32) | lo) >> (sh & 31)); }
 HC_DEV void sts32_if(bool p, u32 a, u32 v) { if (p) sts32(a, v); }
+HC_DEV void atomic_or_smem(u32 a, u32 v) { sts32(a, lds32(a) | v); }
 HC_DEV uint4 ldg16(const void *p) { uint4 v; memcpy(&v, p, 16); return v; }
 HC_DEV uint4 ldg16_rw(const void *p) { uint4 v; memcpy(&v, p, 16); return v; }
 HC_DEV void stg16(void *p, uint4 v) { memcpy(p, &v, 16); }
@@ -172,6 +197,8 @@ HC_DEV u64 shfl_up64(u64 v, unsigned d) { return __shfl_up_sync(FULL, v, d); }
 HC_DEV u64 shfl_down64(u64 v, unsigned d) { return __shfl_down_sync(FULL, v, d); }
 HC_DEV u64 shfl_xor64(u64 v, unsigned m) { return __shfl_xor_sync(FULL, v, m); }
 HC_DEV u32 ballot(bool p) { return __ballot_sync(FULL, p); }
+HC_DEV u32 reduce_max(u32 v) { return __reduce_max_sync(FULL, v); }     // REDUX.MAX.U32: one instruction, uniform result
+HC_DEV u32 reduce_min(u32 v) { return __reduce_min_sync(FULL, v); }
 HC_DEV int popc(u32 v) { return __popc(v); }
 HC_DEV int popcll(u64 v) { return __popcll(v); }
 HC_DEV int clz(u32 v) { return __clz((int)v); }
@@ -216,6 +243,8 @@ HC_DEV void sts32_if(bool p, u32 a, u32 v)
 {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u32 [%0], %1; }" :: "r"(a), "r"(v), "r"((u32)p) : "memory");
 }
+// OR into a shared-memory word by shared-space address, no return value (RED)
+HC_DEV void atomic_or_smem(u32 a, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 // streaming 16-byte load: read-only path, do not allocate in L1 (data is touched once)
 HC_DEV uint4 ldg16(const void *p)
 {

@@ -11,7 +11,11 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("HC_B200_LIB", os.path.join(HERE, "libhc_b200.so"))   # override: kernel experiments only
+LIB_PATH = os.path.join(HERE, "libhc_b200.so")
+# Kernel debugging only (e.g. a -DHC_FGK_CHECK build of the same sources): honoured only together with
+# HC_B200_DEBUG=1, and never for anything that is not a CUDA build of this library (see lib()).
+if os.environ.get("HC_B200_DEBUG") == "1" and os.environ.get("HC_B200_LIB"):
+    LIB_PATH = os.environ["HC_B200_LIB"]
 
 u8p = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)
@@ -83,6 +87,8 @@ def lib():
                 "libhc_b200.so is missing (%s); build it with `python -c 'import __graft_entry__ as g; g.build()'`."
                 " There is no CPU fallback." % LIB_PATH)
         _LIB = bind(LIB_PATH)
+        if b"sm_100a" not in _LIB.hc_version():
+            raise RuntimeError("%s is not a CUDA build of libhc_b200 (%r)" % (LIB_PATH, _LIB.hc_version()))
     return _LIB
 
 
@@ -175,12 +181,21 @@ class Codec:
         return rc, out, out_off, out_len, status
 
     def decompress(self, files, out_cap=None):
+        """-> (list of arrays, status).  A file that does not fit the first buffer comes back with status
+        HC_E_CAPACITY and the size it needs, so one second call with the exact total settles it; anything
+        beyond 255 x the input (no MNP-5 token expands further) stays that file's error."""
         buf, offs, lens = self.pack(files)
-        cap = out_cap if out_cap is not None else max(1 << 20, 8 * int(lens.sum()))
-        while True:
+        in_total = int(lens.sum())
+        cap = out_cap if out_cap is not None else max(1 << 20, 8 * in_total)
+        ceiling = 255 * in_total + 16 * len(files) + 4096
+        for attempt in range(2):
             rc, out, oo, ol, st = self.decompress_packed(buf, offs, lens, cap)
-            if rc == HC_E_CAPACITY:
-                cap *= 4
-                continue
             check(rc, "hc_decompress_batch", self.L)
-            return [out[int(o):int(o) + int(n)].copy() for o, n in zip(oo, ol)], st
+            if attempt == 0 and (st == HC_E_CAPACITY).any():
+                need = int(sum(align_up(int(n), 16) for n, s in zip(ol, st) if s in (0, HC_E_CAPACITY)))
+                if need <= ceiling:
+                    cap = need + 4096
+                    continue
+            break
+        res = [out[int(o):int(o) + int(n)].copy() if s == 0 else np.zeros(0, np.uint8) for o, n, s in zip(oo, ol, st)]
+        return res, st

@@ -91,16 +91,27 @@ std::vector<std::vector<uint8_t>> Codec::huffDecompressBatch(const std::vector<s
 {
     const uint32_t nf = (uint32_t)files.size();
     Packed p = pack(files);
-    uint64_t cap = 1 << 20;
-    for (auto n : p.len) cap += 8 * n;
-    for (;;) {
+    // First try with a generous guess; a file that does not fit comes back with HC_E_CAPACITY and the size it
+    // needs in len[f], so ONE second call with the exact total settles it.  Hard ceiling: an MNP-5 token
+    // expands to at most 255 bytes, anything beyond 255 x input is reported as that file's error.
+    uint64_t in_total = 0;
+    for (auto n : p.len) in_total += n;
+    uint64_t cap = (1 << 20) + 8 * in_total;
+    const uint64_t ceiling = 255 * in_total + 16 * (uint64_t)nf + 4096;
+    for (int attempt = 0;; attempt++) {
         std::vector<uint8_t> out(cap);
         std::vector<uint64_t> off(nf), len(nf);
         std::vector<int32_t> st(nf);
         int rc = hc_decompress_batch((hc_codec *)h_, p.buf.data(), p.off.data(), p.len.data(), nf, out.data(), out.size(), off.data(),
                                      len.data(), st.data());
-        if (rc == HC_E_CAPACITY) { cap *= 4; continue; }     // RLE can expand up to 64x
         throwIf(rc, "hc_decompress_batch");
+        uint64_t need = 0;
+        bool retry = false;
+        for (uint32_t f = 0; f < nf; f++) {
+            if (st[f] == HC_E_CAPACITY) retry = true;
+            if (st[f] == 0 || st[f] == HC_E_CAPACITY) need += (len[f] + 15) / 16 * 16;
+        }
+        if (retry && attempt == 0 && need <= ceiling) { cap = need + 4096; continue; }
         status.assign(st.begin(), st.end());
         return unpack(out, off, len, st);
     }

@@ -170,7 +170,11 @@ int hc_compress_batch(hc_codec *c,
                       uint64_t *out_off, uint64_t *out_len, int32_t *status);
 
 /* huffDecompress, src/main.cpp:90-128, for nf .out files; same buffer conventions.
- * status[f]: 0, 8, 9, 10, 11, 13, 14, 15. */
+ * status[f]: 0, 8, 9, 10, 11, 13, 14, 15, or HC_E_CAPACITY for a file that does not fit what is left of
+ * out_base (out_len[f] = the size it needs; the other files of the batch are decoded normally -- the call
+ * itself still returns 0).  Crafted adaptive headers that promise more than 255 output bytes per payload
+ * byte (no MNP-5 token expands further; the reference dies in its allocation, src/transform.cpp:340) are
+ * walked for their error code (13 / 14) and never sized. */
 int hc_decompress_batch(hc_codec *c,
                         const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
                         uint32_t nf,

@@ -2,7 +2,7 @@
 
 `cuda` : the product library libhc_b200.so with torch-allocated device memory (needs a GPU).
 `emu`  : tests/emu/_build/libhc_emu.so -- the SAME kernel source compiled with -DHC_EMU and
-         executed by the fiber-based SIMT emulator (huffman-codec_b200/csrc/hc_emu.h); "device"
+         executed by the fiber-based SIMT emulator (tests/emu/hc_emu.h); "device"
          memory is host memory.  It exists so that kernel logic is checked on the CPU box
          before GPU minutes are spent; it is a test double, never a product path.
 """
@@ -21,12 +21,14 @@ CSRC = os.path.join(ROOT, "huffman-codec_b200", "csrc")
 
 
 def build_emu(force=False):
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    emu_src = os.path.join(ROOT, "tests", "emu")
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs += [os.path.join(emu_src, f) for f in os.listdir(emu_src) if f.endswith(".h")]
     if not force and os.path.exists(EMU_SO) and all(os.path.getmtime(EMU_SO) >= os.path.getmtime(s) for s in srcs):
         return EMU_SO
     os.makedirs(EMU_DIR, exist_ok=True)
     subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-DHC_EMU", "-x", "c++", "-fPIC", "-shared",
-                    "-Wno-unknown-pragmas", "-o", EMU_SO, os.path.join(CSRC, "hc_api.cu")], check=True)
+                    "-Wno-unknown-pragmas", "-I", emu_src, "-o", EMU_SO, os.path.join(CSRC, "hc_api.cu")], check=True)
     return EMU_SO
 
 

@@ -11,6 +11,9 @@
 #endif
 
 #include <ucontext.h>
+#ifdef HC_EMU_DEBUG
+#include <dlfcn.h>
+#endif
 
 #include <cstdint>
 #include <cstdio>
@@ -43,6 +46,7 @@ struct Fiber {
 struct Warp {
     uint32_t live = 0, arrived = 0, gen = 0;
     uint64_t buf[32], snap[32];
+    void *site[32];          // HC_EMU_DEBUG: caller of the collective each lane is waiting in
 };
 
 struct State {
@@ -82,6 +86,28 @@ inline void bar_release_if_complete()
 inline void warp_release_if_complete(Warp &w)
 {
     if (w.arrived != 0 && (w.arrived & w.live) == w.live) {
+#ifdef HC_EMU_DEBUG
+        // every lane of a converged warp must be inside the SAME collective call
+        void *first = nullptr;
+        for (int i = 0; i < 32; i++)
+            if ((w.live >> i) & 1) {
+                if (!first) first = w.site[i];
+                else if (w.site[i] != first) {
+                    fprintf(stderr, "hc_emu: lanes of a warp wait in different collectives:");
+                    for (int j = 0; j < 32; j++)
+                        if (((w.live >> j) & 1) && (j < 2 || w.site[j] != w.site[j - 1])) {
+                            Dl_info di;
+                            if (dladdr(w.site[j], &di) && di.dli_sname)
+                                fprintf(stderr, "\n  lane %d: %s+0x%lx (lib offset 0x%lx)", j, di.dli_sname, (unsigned long)((char *)w.site[j] - (char *)di.dli_saddr),
+                                        (unsigned long)((char *)w.site[j] - (char *)di.dli_fbase));
+                            else
+                                fprintf(stderr, "\n  lane %d: %p (lib offset 0x%lx)", j, w.site[j], di.dli_fbase ? (unsigned long)((char *)w.site[j] - (char *)di.dli_fbase) : 0ul);
+                        }
+                    fprintf(stderr, "\n");
+                    abort();
+                }
+            }
+#endif
         memcpy(w.snap, w.buf, sizeof w.snap);
         w.arrived = 0;
         w.gen++;
@@ -112,13 +138,14 @@ inline void syncthreads()
 }
 
 // all live lanes of the calling warp exchange one 64-bit value; returns pointer to the snapshot
-inline const uint64_t *warp_exchange(uint64_t v)
+inline const uint64_t *warp_exchange(uint64_t v, void *site = nullptr)
 {
     State &s = st();
     unsigned tid = s.cur;
     Warp &w = s.warps[tid / 32];
     unsigned g = w.gen;
     w.buf[tid % 32] = v;
+    w.site[tid % 32] = site;
     w.arrived |= 1u << (tid % 32);
     warp_release_if_complete(w);
     while (w.gen == g) yield();

@@ -414,6 +414,10 @@ def _fgk_stress_inputs(be):
             p = rng.dirichlet(np.full(64, 0.08))
             f = rng.choice(64, n, p=p) * 3
         files.append(np.asarray(f, np.uint8))
+    # one long stream of short runs over the full alphabet: many subtree swaps, two in one update now and then
+    # (a leaf can come back to the same path through different nodes -- the encoder's lookup-ahead must notice)
+    n = 40000 if be.name == "emu" else 400000
+    files.append(np.repeat(rng.integers(0, 256, n // 7 + 1), 7)[:n].astype(np.uint8))
     return files
 
 
