@@ -85,7 +85,6 @@ struct FgkCtx {              // shared addresses (identical in every lane) + per
     u32 rec, spf, pfx, pt, buf, ring;
     u32 nyt;                 // offset of the NYT node
     u32 lev;                 // number of populated levels of pt
-    u32 gen;                 // bumped whenever pt may have changed (the decoder's prefetched lookup is then redone)
     u32 err;                 // set when a walk does not end (cannot happen on a consistent tree): the stream fails with status 102
     u32 ptj, shj;            // lane j: address of its level of pt, shift that turns a left-aligned path into its index
 };
@@ -103,7 +102,6 @@ HC_DEV void fgk_init(FgkCtx &c, FgkTree &t, u32 lane)
     c.ring = smem_addr(&t.ring[0]);
     c.nyt = FGK_ROOT_O;
     c.lev = 0;
-    c.gen = 0;
     c.err = 0;
     c.ptj = c.pt + (lane < FGK_D ? 2u * ((2u << lane) - 2u) : 0u);
     c.shj = lane < FGK_D ? FGK_D - 1u - lane : 0u;
@@ -170,7 +168,6 @@ HC_DEV void fgk_rebuild(FgkCtx &c, u32 lane)
         lev = d;
     }
     c.lev = lev;
-    c.gen++;
     syncwarp();
 }
 
@@ -244,7 +241,6 @@ HC_DEV void fgk_table_split(FgkCtx &c, u32 n, u32 pn, u32 lane)
         fgk_set_pfx(c, child, (d << 12) | (p << (FGK_D - d)));
     }
     if (d > c.lev) c.lev = d;
-    c.gen++;
     syncwarp();
 }
 
@@ -353,7 +349,7 @@ HC_DEV_NOINLINE FgkCtx fgk_update_seq(FgkCtx c, u32 a, u32 lane)
 constexpr u32 FGK_I_NOSWAP = 1u << 16;    // the leader is the node's parent: plain increment
 constexpr u32 FGK_I_SAMEP = 1u << 17;     // leader and node share the parent: the path above is unchanged
 constexpr u32 FGK_I_SC = 1u << 18;        // an internal node moves: table entries below the two nodes change
-constexpr u32 FGK_I_LONG = 1u << 20;      // more than two equal weights: leader search
+constexpr u32 FGK_I_LONG = 1u << 20;      // more than two equal weights: leader search (bits 0..15 = the node, not a pfx)
 constexpr u32 FGK_I_TIE = 1u << 26;
 
 struct FgkPre {          // what a lane loads about its node A per round
@@ -374,8 +370,7 @@ HC_DEV FgkPre fgk_preload(const FgkCtx &c, u32 A)
 }
 
 // description of the swap of the node with record word y (parent | down << 16) with the leader at
-// offset l (record word yl, pfx pfl).  Branch free on purpose: with an `if (tie)` around it ptxas sinks
-// the loads into the branch and the tied lanes pay a second shared-memory round trip before the REDUX.
+// offset l (record word yl, pfx pfl)
 HC_DEV u32 fgk_swap_info(u32 y, u32 yl, u32 l, u32 pfl)
 {
     u32 info = pfl;
@@ -386,28 +381,24 @@ HC_DEV u32 fgk_swap_info(u32 y, u32 yl, u32 l, u32 pfl)
 }
 static_assert(FGK_I_SC == (0x80000000u >> 13), "bit trick above");
 
-// FGK update of a node whose path is in the table (src/huffman.cpp:113-127).  A = this lane's node
-// (fgk_lookup of pf), pf = depth << 12 | left-aligned path of the node the update starts from.
-// `have`: the caller already did this round's loads (`pre`).
-HC_DEV void fgk_update_rounds(FgkCtx &c, u32 A, u32 pf, u32 lane, bool have, FgkPre pre)
+// The part of the update that is only entered when some level of the path ties with the node after it
+// (src/huffman.cpp:115-125: leader search, swap, continue from the leader's parent).  Same arguments
+// as fgk_update; `pre` holds this round's loads.
+HC_DEV void fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
 {
     const u32 lanebits = (lane << 27) | FGK_I_TIE;
     u32 guard = 0;
     for (;;) {
         if (++guard > 600u) { c.err = 1; return; }       // more rounds than nodes: never on a consistent tree
         const u32 depth = pf >> 12;
-        if (!have) pre = fgk_preload(c, A);
-        have = false;
         const u32 W = pre.n.x;
         const bool tie = lane < depth && pre.n1.x == W;
-        const bool lng = tie && pre.w2 == W;
-        const u32 info = tie ? (lanebits | fgk_swap_info(pre.n.y, pre.n1.y, A + 8u, pre.pfl) | (lng ? FGK_I_LONG : 0u)) : 0u;
-        const u32 ainfo = lng ? ((lane << 27) | A) : 0u;
+        const bool lng = pre.w2 == W;
+        const u32 info = tie ? (lanebits | (lng ? (FGK_I_LONG | A) : fgk_swap_info(pre.n.y, pre.n1.y, A + 8u, pre.pfl))) : 0u;
         u32 hi = depth;                                   // lanes [0, hi) still have to add 1 to their node
         bool newpath = false;
         for (;;) {
             u32 r = reduce_max(lane < hi ? info : 0u);
-            const u32 r2 = reduce_max(lane < hi ? ainfo : 0u);
             syncwarp();                                   // this round's loads precede its stores
             if (r == 0u) break;
             const u32 k0 = r >> 27;
@@ -418,8 +409,8 @@ HC_DEV void fgk_update_rounds(FgkCtx &c, u32 A, u32 pf, u32 lane, bool have, Fgk
             u32 a = A, l = A + 8u, y = pre.n.y, yl = pre.n1.y, w = W;
             if (r & FGK_I_LONG) {
                 // a run of three or more equal weights: every lane probes one node of the run, then all
-                // lanes fetch the two nodes of the swap (r2 carries the tied node: it is the deepest long tie)
-                a = r2 & 0xffffu;
+                // lanes fetch the two nodes of the swap
+                a = r & 0xffffu;
                 const uint2 na = lds64(c.rec + a);
                 u32 pa = a + 24u + 8u * lane;
                 pa = pa < FGK_SENT_O ? pa : FGK_SENT_O;
@@ -427,7 +418,7 @@ HC_DEV void fgk_update_rounds(FgkCtx &c, u32 A, u32 pf, u32 lane, bool have, Fgk
                 l = m ? a + 8u + 8u * (u32)ffs(m) : fgk_leader(c, a + 24u + 256u, na.x, lane);
                 y = na.y; w = na.x;
                 yl = lds32(c.rec + l + 4u);
-                r = (r & 0xf8000000u) | fgk_swap_info(y, yl, l, lds16(c.pfx + (l >> 2)));
+                r = fgk_swap_info(y, yl, l, lds16(c.pfx + (l >> 2)));
                 syncwarp();                               // these loads precede the tied lane's stores
             }
             const u32 pfl = r & 0xffffu;
@@ -456,7 +447,6 @@ HC_DEV void fgk_update_rounds(FgkCtx &c, u32 A, u32 pf, u32 lane, bool have, Fgk
                 // the old node is level k0 of this path, the leader's path came with r
                 const u32 sh = FGK_D - 1u - k0;
                 c.lev = fgk_rebuild_pair_cold(c, ((k0 + 1u) << 12) | (((pf & 0x1ffu) >> sh) << sh), pfl, lane);
-                c.gen++;
             } else if (r & FGK_I_SAMEP) {
                 continue;                                 // same parent: the levels above are as loaded
             }
@@ -464,7 +454,6 @@ HC_DEV void fgk_update_rounds(FgkCtx &c, u32 A, u32 pf, u32 lane, bool have, Fgk
                 // the leader lies deeper than the table: finish sequentially from its parent
                 const u32 pl = shfl(fgk_parent(yl), (int)k0);
                 c = fgk_update_seq(c, pl, lane);
-                c.gen++;
                 return;
             }
             if ((pfl >> 12) == 1u) { hi = 0; break; }     // the leader hangs below the root: done
@@ -473,11 +462,30 @@ HC_DEV void fgk_update_rounds(FgkCtx &c, u32 A, u32 pf, u32 lane, bool have, Fgk
             newpath = true;
             break;
         }
-        if (newpath) continue;
-        sts32_if(lane < hi, c.rec + A, W + 1u);
+        if (!newpath) {
+            sts32_if(lane < hi, c.rec + A, W + 1u);
+            syncwarp();
+            return;
+        }
+        pre = fgk_preload(c, A);
+    }
+}
+
+// FGK update of a node whose path is in the table (src/huffman.cpp:113-127).  A = this lane's node
+// (fgk_lookup of pf), pf = depth << 12 | left-aligned path of the node the update starts from, `pre` =
+// fgk_preload(A).  Most symbols take the first exit: no level ties, every lane adds 1 to its node.
+HC_DEV void fgk_update(FgkCtx &c, u32 A, u32 pf, u32 lane, const FgkPre &pre)
+{
+    const bool valid = lane < (pf >> 12);
+    const bool tie = valid && pre.n1.x == pre.n.x;
+    const bool some = any(tie);
+    syncwarp();                                           // the loads precede the stores
+    if (!some) {
+        sts32_if(valid, c.rec + A, pre.n.x + 1u);
         syncwarp();
         return;
     }
+    fgk_update_ties(c, A, pf, lane, pre);
 }
 
 #if defined(HC_EMU_DEBUG) || defined(HC_FGK_CHECK)
@@ -688,78 +696,54 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
     bw_put(c, bw, flags ? flags[f] : 0u, 8, lane);
 
     bool too_long = too_many;
-    // symbols are staged 128 at a time (4 per lane) in a two-half ring, one chunk ahead, so that the
-    // lookups of the next symbol can run ahead of the update across chunk boundaries
-    u32 cnext = 0;
-    if (m > 0) sts32(c.buf + 4u * lane, ldg32(src + lane));
-    if (m > 128) cnext = ldg32(src + 32 + lane);
-    syncwarp();
-    // software pipeline: symbol -> spf (leaf, code) -> per-lane nodes of its path (A), one symbol ahead
-    u32 y0 = lds8(c.buf), y1 = lds8(c.buf + 1u);
-    u32 sp0 = lds32(c.spf + 4u * y0);
-    u32 A0 = fgk_lookup(c, sp0 >> 16);
-    u32 gen0 = c.gen;                                     // table generation A0 was looked up in
+    // symbols are staged 128 at a time (4 per lane, the next chunk already on its way from global memory);
+    // table codes are parked in lane (symbol index mod 32) and packed by the warp every 32 symbols
+    u32 cnext = m > 0 ? ldg32(src + lane) : 0u;
     u32 code = 0;                                         // this lane's parked table code
     for (u32 i0 = 0; i0 < m; i0 += 128) {
-        syncwarp();                                       // every lane is done with the half that is overwritten
-        sts32(c.buf + ((i0 + 128u) & 128u) + 4u * lane, cnext);
+        syncwarp();                                       // every lane is done with the previous chunk
+        sts32(c.buf + 4u * lane, cnext);
         syncwarp();
-        if (i0 + 256u < m) cnext = ldg32(src + (i0 + 256u) / 4u + lane);   // prefetch the chunk after the next
+        if (i0 + 128u < m) cnext = ldg32(src + (i0 + 128u) / 4u + lane);
         const u32 cnt = (m - i0) < 128u ? (m - i0) : 128u;
-        for (u32 i = 0; i < cnt; i++) {
-            // The entry of this symbol was fetched one symbol ago, before the previous update: re-read it (a
-            // leaf that moved shows up as a different word) and compare the table generation (two subtree
-            // swaps in one update can bring a leaf back to the same path through different nodes).  The next
-            // symbol's lookups are issued before this symbol's update.
-            const u32 chk = lds32(c.spf + 4u * y0);
-            const u32 sp1 = lds32(c.spf + 4u * y1);
-            const u32 y2 = lds8(c.buf + ((i0 + i + 2u) & 255u));
-            FgkPre pre = fgk_preload(c, A0);
-            const u32 A1 = fgk_lookup(c, sp1 >> 16);
-            const u32 gen1 = c.gen;
-            bool have = true;
-            if (chk != sp0 || gen0 != gen1) {
-                sp0 = chk;
-                A0 = fgk_lookup(c, sp0 >> 16);
-                have = false;
-            }
-            const u32 pf0 = sp0 >> 16;
-            if (pf0 == FGK_NOPATH) {
-                // Not yet transmitted, or deeper than the table.  Encode precedes update (src/transform.cpp:372-375):
-                // the code is read off the tree first, by a parent chase; a new symbol sends the NYT code + 8 raw
-                // bits (src/huffman.cpp:42-51), then splits.
-                bw_pack(c, bw, code, lane);
-                code = 0;
-                const bool isnew = sp0 == FGK_SPF_NONE;
-                u32 hi = 0x80000000u, lo = 0u, start = sp0 & 0xffffu;
-                fgk_code_of(c, isnew ? c.nyt : start, hi, lo);
-                if (!bw_put_code(c, bw, hi, lo, lane)) too_long = true;
-                if (isnew) {
-                    bw_put(c, bw, y0, 8, lane);
-                    const u32 n = c.nyt, pn = n == FGK_ROOT_O ? 0u : lds16(c.pfx + (n >> 2));
-                    start = fgk_split(c, y0, lane);
-                    fgk_table_split(c, n, pn, lane);
+        for (u32 g0 = 0; g0 < cnt; g0 += 32) {
+            const u32 gcnt = (cnt - g0) < 32u ? (cnt - g0) : 32u;
+            for (u32 j = 0; j < gcnt; j++) {
+                const u32 y = lds8(c.buf + g0 + j);
+                const u32 sp = lds32(c.spf + 4u * y);
+                const u32 pf = sp >> 16;
+                if (pf == FGK_NOPATH) {
+                    // Not yet transmitted, or deeper than the table.  Encode precedes update (src/transform.cpp:372-375):
+                    // the code is read off the tree first, by a parent chase; a new symbol sends the NYT code + 8 raw
+                    // bits (src/huffman.cpp:42-51), then splits.
+                    bw_pack(c, bw, code, lane);
+                    code = 0;
+                    const bool isnew = sp == FGK_SPF_NONE;
+                    u32 hi = 0x80000000u, lo = 0u, start = sp & 0xffffu;
+                    fgk_code_of(c, isnew ? c.nyt : start, hi, lo);
+                    if (!bw_put_code(c, bw, hi, lo, lane)) too_long = true;
+                    if (isnew) {
+                        bw_put(c, bw, y, 8, lane);
+                        const u32 n = c.nyt, pn = n == FGK_ROOT_O ? 0u : lds16(c.pfx + (n >> 2));
+                        start = fgk_split(c, y, lane);
+                        fgk_table_split(c, n, pn, lane);
+                    }
+                    c = fgk_update_seq(c, start, lane);
+                } else {
+                    // the code of a leaf is its path (encode precedes update, src/transform.cpp:372-375)
+                    if (lane == j) code = pf;
+                    const u32 A = fgk_lookup(c, pf);
+                    fgk_update(c, A, pf, lane, fgk_preload(c, A));
                 }
-                c = fgk_update_seq(c, start, lane);
-            } else {
-                // the code of a leaf is its path (encode precedes update, src/transform.cpp:372-375)
-                if (lane == ((i0 + i) & 31u)) code = pf0;
-                fgk_update_rounds(c, A0, pf0, lane, have, pre);
-            }
-            if (((i0 + i) & 31u) == 31u) {
-                bw_pack(c, bw, code, lane);
-                code = 0;
-            }
 #if defined(HC_EMU_DEBUG) || defined(HC_FGK_CHECK)
-            syncwarp();
-            if (!c.err && ballot(!fgk_validate(c, lane, i0 + i))) { c.err = 2; }
-            syncwarp();
-            if (c.err) { i0 = m; break; }
+                syncwarp();
+                if (!c.err && ballot(!fgk_validate(c, lane, i0 + g0 + j))) c.err = 2;
+                syncwarp();
 #endif
-            y0 = y1; y1 = y2;
-            sp0 = sp1;
-            A0 = A1;
-            gen0 = gen1;
+            }
+            bw_pack(c, bw, code, lane);
+            code = 0;
+            if (c.err) { i0 = m; break; }
         }
     }
     bw_pack(c, bw, code, lane);
@@ -900,33 +884,24 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     u32 *dst = (u32 *)(sym + sym_off[f]);
     const u32 shd = 31u - (lane < FGK_D ? lane : 0u);
     const u32 lanekey = lane << 16;
-    u32 e = 0;
-    bool have_e = false;
     for (u32 i = 0; i < m; i++) {
         // The path table resolves the next FGK_D code bits in one step: lane j looks up the node that
         // the first j + 1 bits lead to; the shallowest leaf among them ends the code (REDUX.MIN over
         // lane << 16 | symbol).  The loads of the update's first round ride on the same round of loads.
         const u32 t = (u32)(br.win >> 32);
-        if (!have_e) e = lane < FGK_D ? lds16(c.ptj + 2u * (t >> shd)) : FGK_ROOT_O;
-        have_e = false;
+        const u32 e = lane < FGK_D ? lds16(c.ptj + 2u * (t >> shd)) : FGK_ROOT_O;
         const FgkPre pre = fgk_preload(c, e);
         const u32 ka = fgk_down(pre.n.y);
         const u32 r = reduce_min((e != FGK_ROOT_O && (ka & FGK_LEAF)) ? (lanekey | (ka & 0x1ffu)) : 0xffffffffu);
         u32 y;
         if (r == 0xffffffffu || (r & 0x100u)) {
             y = fgk_decode_cold(c, br, lane);
+            if (c.err) break;
         } else {
             const u32 depth = (r >> 16) + 1u;
             y = r & 0xffu;
             br_skip(br, depth, lane);
-            // the next code starts here: its table lookup does not depend on this symbol's update
-            // unless the tree changes shape (c.gen moves)
-            const u32 t2 = (u32)(br.win >> 32);
-            const u32 e2 = lane < FGK_D ? lds16(c.ptj + 2u * (t2 >> shd)) : FGK_ROOT_O;
-            const u32 gen = c.gen;
-            fgk_update_rounds(c, e, (depth << 12) | (t >> 23), lane, true, pre);
-            e = e2;
-            have_e = gen == c.gen;
+            fgk_update(c, e, (depth << 12) | (t >> 23), lane, pre);
         }
         if (lane == 0) sts8(c.buf + (i & 127u), y);
         if ((i & 127u) == 127u) {

@@ -107,6 +107,14 @@ HC_DEV u32 reduce_max(u32 v)
         if (((live >> i) & 1) && (u32)s[i] > r) r = (u32)s[i];
     return r;
 }
+HC_DEV bool any(bool p)
+{
+    const u64 *s = hc_emu::warp_exchange(p ? 1 : 0 HC_SITE);
+    u32 live = hc_emu::warp_live();
+    for (int i = 0; i < 32; i++)
+        if (((live >> i) & 1) && s[i]) return true;
+    return false;
+}
 HC_DEV u32 reduce_min(u32 v)
 {
     const u64 *s = hc_emu::warp_exchange(v HC_SITE);
@@ -197,6 +205,7 @@ HC_DEV u64 shfl_up64(u64 v, unsigned d) { return __shfl_up_sync(FULL, v, d); }
 HC_DEV u64 shfl_down64(u64 v, unsigned d) { return __shfl_down_sync(FULL, v, d); }
 HC_DEV u64 shfl_xor64(u64 v, unsigned m) { return __shfl_xor_sync(FULL, v, m); }
 HC_DEV u32 ballot(bool p) { return __ballot_sync(FULL, p); }
+HC_DEV bool any(bool p) { return __any_sync(FULL, p) != 0; }            // VOTE.ANY with a predicate result
 HC_DEV u32 reduce_max(u32 v) { return __reduce_max_sync(FULL, v); }     // REDUX.MAX.U32: one instruction, uniform result
 HC_DEV u32 reduce_min(u32 v) { return __reduce_min_sync(FULL, v); }
 HC_DEV int popc(u32 v) { return __popc(v); }
