@@ -7,7 +7,16 @@
 #include "../../include/hc_b200.h"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <thread>
+#ifndef HC_EMU
+#include <dlfcn.h>
+#endif
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -1062,5 +1071,189 @@ extern "C" int hc_decompress_batch(hc_codec *c,
         if (oversize[i]) { status[i] = HC_E_CAPACITY; out_len[i] = need[i]; }
         else if (status[i] != 0) out_len[i] = 0;
     }
+    return 0;
+}
+
+// ======================================================================= asynchronous pipeline
+struct hc_pipeline {
+    struct Slot {
+        hc_codec *codec = nullptr;
+        std::thread worker;
+        std::deque<std::pair<int64_t, std::function<int()>>> jobs;
+    };
+    std::vector<Slot> slots;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::map<int64_t, int> done;
+    int64_t next_ticket = 0;
+    bool stop = false;
+};
+
+static void pipeline_worker(hc_pipeline *p, size_t si)
+{
+    for (;;) {
+        std::pair<int64_t, std::function<int()>> job;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_job.wait(lk, [&] { return p->stop || !p->slots[si].jobs.empty(); });
+            if (p->slots[si].jobs.empty()) return;
+            job = std::move(p->slots[si].jobs.front());
+            p->slots[si].jobs.pop_front();
+        }
+        const int rc = job.second();
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->done[job.first] = rc;
+        }
+        p->cv_done.notify_all();
+    }
+}
+
+extern "C" int hc_pipeline_create(hc_pipeline **out, int device, int depth)
+{
+    if (depth < 1) depth = 1;
+    if (depth > 8) depth = 8;
+    hc_pipeline *p = new hc_pipeline();
+    p->slots.resize((size_t)depth);
+    for (int i = 0; i < depth; i++) {
+        int rc = hc_codec_create(&p->slots[(size_t)i].codec, device);
+        if (rc) {
+            for (int k = 0; k < i; k++) hc_codec_destroy(p->slots[(size_t)k].codec);
+            delete p;
+            return rc;
+        }
+    }
+    for (int i = 0; i < depth; i++) p->slots[(size_t)i].worker = std::thread(pipeline_worker, p, (size_t)i);
+    *out = p;
+    return 0;
+}
+
+extern "C" void hc_pipeline_destroy(hc_pipeline *p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+    }
+    p->cv_job.notify_all();
+    for (auto &s : p->slots) if (s.worker.joinable()) s.worker.join();      // pending jobs are finished first
+    for (auto &s : p->slots) hc_codec_destroy(s.codec);
+    delete p;
+}
+
+static int64_t pipeline_submit(hc_pipeline *p, std::function<int(hc_codec *)> fn)
+{
+    int64_t t;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (p->stop) return -1;
+        t = p->next_ticket++;
+        hc_pipeline::Slot &s = p->slots[(size_t)(t % (int64_t)p->slots.size())];
+        hc_codec *c = s.codec;
+        s.jobs.emplace_back(t, [fn, c] { return fn(c); });
+    }
+    p->cv_job.notify_all();
+    return t;
+}
+
+extern "C" int64_t hc_pipeline_submit_compress(hc_pipeline *p,
+                                               const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                               uint32_t nf, int use_diff, int use_adapt, const uint64_t *width_host,
+                                               uint8_t *out_base, uint64_t out_cap_total,
+                                               uint64_t *out_off, uint64_t *out_len, int32_t *status)
+{
+    return pipeline_submit(p, [=](hc_codec *c) {
+        return hc_compress_batch(c, in_base, in_off, in_len, nf, use_diff, use_adapt, width_host, out_base, out_cap_total, out_off,
+                                 out_len, status);
+    });
+}
+
+extern "C" int64_t hc_pipeline_submit_decompress(hc_pipeline *p,
+                                                 const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                                 uint32_t nf,
+                                                 uint8_t *out_base, uint64_t out_cap_total,
+                                                 uint64_t *out_off, uint64_t *out_len, int32_t *status)
+{
+    return pipeline_submit(p, [=](hc_codec *c) {
+        return hc_decompress_batch(c, in_base, in_off, in_len, nf, out_base, out_cap_total, out_off, out_len, status);
+    });
+}
+
+extern "C" int hc_pipeline_wait(hc_pipeline *p, int64_t ticket)
+{
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (ticket < 0 || ticket >= p->next_ticket) return -1;
+    p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });
+    const int rc = p->done[ticket];
+    p->done.erase(ticket);
+    return rc;
+}
+
+// ======================================================================= multi-GPU: size all-gather
+namespace hcd {
+// padded all-gather result (world x per) -> global file order
+HC_KERNEL shard_unpad_kernel(const u64 *HC_RESTRICT padded, u64 *HC_RESTRICT all, u32 n_total, u32 world, u32 per)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const u32 base = n_total / world, extra = n_total % world;
+    // owner of file i under the contiguous split (the first `extra` ranks own base + 1 files)
+    const u32 cut = extra * (base + 1u);
+    const u32 r = i < cut ? i / (base + 1u) : extra + (base ? (i - cut) / base : 0u);
+    const u32 lo = r * base + (r < extra ? r : extra);
+    all[i] = padded[(u64)r * per + (i - lo)];
+}
+HC_KERNEL shard_pad_kernel(const u64 *HC_RESTRICT local, u64 *HC_RESTRICT padded, u32 n_local, u32 per)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < per) padded[i] = i < n_local ? local[i] : 0;
+}
+}  // namespace hcd
+
+extern "C" uint64_t hc_shard_ws_bytes(uint32_t n_total, int world)
+{
+    if (world < 1) world = 1;
+    const uint64_t per = (n_total + (uint32_t)world - 1) / (uint32_t)world;
+    return (per * ((uint64_t)world + 1) + 8) * 8;
+}
+
+extern "C" int hc_shard_sizes_allgather(void *nccl_comm, int rank, int world,
+                                        const uint64_t *d_local_sizes, uint32_t n_total, uint32_t align,
+                                        uint64_t *d_all_sizes, uint64_t *d_offsets, uint64_t *d_total,
+                                        void *ws, hc_stream_t stream)
+{
+    if (world < 1 || rank < 0 || rank >= world) return -1;
+    if (n_total == 0) return 0;
+    const u32 base = n_total / (u32)world, extra = n_total % (u32)world;
+    const u32 n_local = base + ((u32)rank < extra ? 1u : 0u);
+    const u32 per = (n_total + (u32)world - 1) / (u32)world;
+    u64 *send = (u64 *)ws, *recv = send + per;
+    HC_LAUNCH(shard_pad_kernel, dim3((per + 255) / 256), dim3(256), 0, stream, d_local_sizes, send, n_local, per);
+    HC_CHECK_LAUNCH();
+    if (world == 1) {
+        HC_CUDA(cudaMemcpyAsync(recv, send, (size_t)per * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    } else {
+#ifdef HC_EMU
+        (void)nccl_comm;
+        return HC_E_NCCL - 999;
+#else
+        // ncclAllGather(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t); ncclUint64 = 5
+        typedef int (*allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+        static allgather_fn fn = nullptr;
+        if (!fn) {
+            fn = (allgather_fn)dlsym(RTLD_DEFAULT, "ncclAllGather");       // the NCCL this process already uses
+            if (!fn) {
+                void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+                if (h) fn = (allgather_fn)dlsym(h, "ncclAllGather");
+            }
+            if (!fn) return HC_E_NCCL - 999;
+        }
+        const int rc = fn(send, recv, per, 5, nccl_comm, (cudaStream_t)stream);
+        if (rc != 0) return HC_E_NCCL - rc;
+#endif
+    }
+    HC_LAUNCH(shard_unpad_kernel, dim3((n_total + 255) / 256), dim3(256), 0, stream, (const u64 *)recv, d_all_sizes, n_total, (u32)world, per);
+    HC_CHECK_LAUNCH();
+    if (d_offsets) return hc_offsets_from_lens(d_all_sizes, d_offsets, d_total, n_total, align ? align : 1u, stream);
     return 0;
 }

@@ -58,6 +58,13 @@ SIGNATURES = {
     "hc_decompress_batch": (C.c_int, [vp, vp, vp, vp, u32, vp, u64, vp, vp, vp]),
     "hc_compress_device": (C.c_int, [vp, vp, vp, vp, vp, u32, u64, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
     "hc_decompress_device": (C.c_int, [vp, vp, vp, vp, u32, u64, u64, C.c_int, vp, vp, vp, vp, vp]),
+    "hc_pipeline_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
+    "hc_pipeline_destroy": (None, [vp]),
+    "hc_pipeline_submit_compress": (C.c_int64, [vp, vp, vp, vp, u32, C.c_int, C.c_int, vp, vp, u64, vp, vp, vp]),
+    "hc_pipeline_submit_decompress": (C.c_int64, [vp, vp, vp, vp, u32, vp, u64, vp, vp, vp]),
+    "hc_pipeline_wait": (C.c_int, [vp, C.c_int64]),
+    "hc_shard_ws_bytes": (u64, [u32, C.c_int]),
+    "hc_shard_sizes_allgather": (C.c_int, [vp, C.c_int, C.c_int, vp, u32, u32, vp, vp, vp, vp, vp]),
     "hc_codec_stream": (vp, [vp]),
     "hc_codec_stage_times": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int]),
     "hc_stage_name": (C.c_char_p, [vp, C.c_int]),

@@ -49,6 +49,8 @@ extern "C" {
 #define HC_E_ADAPT_LEFTOVER 15  /* src/transform.cpp:354-358                               */
 #define HC_E_CAPACITY 100       /* output region too small (len[f] then holds the need)    */
 #define HC_E_CODELEN 101        /* FGK code longer than 56 bits (needs > 2^32 symbols)      */
+#define HC_E_INTERNAL 102       /* a tree walk did not end (inconsistent FGK tree): never on valid state */
+#define HC_E_NCCL (-1000)       /* hc_shard_sizes_allgather: -(1000 + ncclResult_t); -1999 = NCCL not loadable */
 
 typedef void *hc_stream_t;
 
@@ -180,6 +182,42 @@ int hc_decompress_batch(hc_codec *c,
                         uint32_t nf,
                         uint8_t *out_base, uint64_t out_cap_total,
                         uint64_t *out_off, uint64_t *out_len, int32_t *status);
+
+/* ---- asynchronous host level: a pipeline of `depth` codecs, each with its own stream, buffers and
+ * worker thread (replaces the one-file-at-a-time `ifs.get()` loading of src/main.cpp:46-51 by batched,
+ * overlapped transfers).  A submit returns at once; the job runs hc_compress_batch / hc_decompress_batch
+ * on the next slot, so the host<->device copies of one batch overlap the kernels of the batches around
+ * it.  Buffers named in a submit must stay valid and untouched until hc_pipeline_wait returns for the
+ * ticket.  Jobs start in submit order; each slot runs one job at a time. */
+typedef struct hc_pipeline hc_pipeline;
+int hc_pipeline_create(hc_pipeline **out, int device, int depth /* 1..8 */);
+void hc_pipeline_destroy(hc_pipeline *p);
+/* same arguments as hc_compress_batch / hc_decompress_batch; returns a ticket >= 0 or a negative error */
+int64_t hc_pipeline_submit_compress(hc_pipeline *p,
+                                    const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                    uint32_t nf, int use_diff, int use_adapt, const uint64_t *width_host,
+                                    uint8_t *out_base, uint64_t out_cap_total,
+                                    uint64_t *out_off, uint64_t *out_len, int32_t *status);
+int64_t hc_pipeline_submit_decompress(hc_pipeline *p,
+                                      const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                      uint32_t nf,
+                                      uint8_t *out_base, uint64_t out_cap_total,
+                                      uint64_t *out_off, uint64_t *out_len, int32_t *status);
+/* blocks until the job has finished; returns what the synchronous call would have returned */
+int hc_pipeline_wait(hc_pipeline *p, int64_t ticket);
+
+/* ---- multi-GPU: the path's only collective.  The batch of n_total files is cut into
+ * contiguous shards (rank r owns files [r*base + min(r, extra), ...), base = n_total / world, extra =
+ * n_total % world); every rank passes the device array of its shard's per-file output sizes and gets
+ * back, in global file order, all sizes, the offsets of the concatenated container (starts aligned to
+ * `align` bytes) and its total size.  `nccl_comm` is an ncclComm_t; the NCCL library already loaded in
+ * the process (or libnccl.so.2) is bound at run time, libhc_b200.so does not link it.  `ws` = device
+ * scratch of hc_shard_ws_bytes() bytes.  Asynchronous on `stream`.  Returns 0, -(cudaError_t) or HC_E_NCCL - code. */
+uint64_t hc_shard_ws_bytes(uint32_t n_total, int world);
+int hc_shard_sizes_allgather(void *nccl_comm, int rank, int world,
+                             const uint64_t *d_local_sizes, uint32_t n_total, uint32_t align,
+                             uint64_t *d_all_sizes, uint64_t *d_offsets, uint64_t *d_total,
+                             void *ws, hc_stream_t stream);
 
 /* device-resident variants used by bench.py's kernel-only timing: inputs already in HBM,
  * outputs left in HBM (d_out compact, 256-byte aligned starts); nothing crosses PCIe and

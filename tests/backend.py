@@ -28,7 +28,7 @@ def build_emu(force=False):
         return EMU_SO
     os.makedirs(EMU_DIR, exist_ok=True)
     subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-DHC_EMU", "-x", "c++", "-fPIC", "-shared",
-                    "-Wno-unknown-pragmas", "-I", emu_src, "-o", EMU_SO, os.path.join(CSRC, "hc_api.cu")], check=True)
+                    "-Wno-unknown-pragmas", "-pthread", "-I", emu_src, "-o", EMU_SO, os.path.join(CSRC, "hc_api.cu")], check=True)
     return EMU_SO
 
 

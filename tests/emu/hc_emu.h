@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 struct uint4 { unsigned x, y, z, w; };
@@ -195,6 +196,9 @@ inline void run_block(unsigned nthreads, const std::function<void()> &body)
 
 inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
 {
+    // one emulated launch at a time (the emulator state is global); host threads of hc_pipeline take turns
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
     State &s = st();
     gridDim = grid;
     blockDim = block;
