@@ -16,9 +16,9 @@ every rank derives the global offsets table.
 
 value   = uncompressed bytes pushed through compress AND decompress by all ranks / device time (CUDA
           events, inputs resident in HBM, max over ranks).  Consecutive steps run on two codec streams
-          (config.overlap = 2): FGK is bound by the latency of its longest stream, so the decompress of
+          (config.overlap = 4): FGK is bound by the latency of its longest stream, so the decompress of
           step s and the compress of step s+1 share the GPU.  `sequential_ms_per_step` = one stream.
-e2e     = same metric through the asynchronous host API (hc_pipeline_*, depth 2) with pinned HOST
+e2e     = same metric through the asynchronous host API (hc_pipeline_*, depth 4) with pinned HOST
           buffers, host<->device copies inside the timed region, all K steps.
 roofline= dominant kernel (FGK: instruction issue, see roofline.note) and, in `stages`, every
           transform kernel's achieved algorithmic GB/s against MEASURED_PEAKS.json:hbm_gbs.
@@ -330,7 +330,7 @@ def run_ours(args):
     d_in_off = torch.arange(nf, dtype=i64, device=dev) * FB
     d_in_len = torch.full((nf,), FB, dtype=i64, device=dev)
     d_width = torch.full((nf,), side, dtype=i64, device=dev)
-    n_arms = max(1, min(args.overlap, 2))
+    n_arms = max(1, min(args.overlap, 4))
     arms = [DeviceArm(torch, hc_b200, L, dev, d_in, d_in_off, d_in_len, d_width, nf, FB, use_adapt) for _ in range(n_arms)]
     A0 = arms[0]
     for arm in arms:                                                  # per stream: scratch + result of the size exchange
@@ -491,13 +491,14 @@ def run_ours(args):
         offs = (np.arange(nf, dtype=np.uint64) * FB)
         lens_h = np.full(nf, FB, np.uint64)
         widths = np.full(nf, side, np.uint64)
-        nbuf = 3
+        pipe = C.c_void_p()
+        depth = max(2, min(args.depth, 8)) & ~1
+        nbuf = depth + 1
         pin_cmp = [torch.empty(out_bytes + 16 * nf + 4096, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
         pin_dec = [torch.empty(nf * FB + 4096, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
         tabs = [[np.zeros(nf, np.uint64), np.zeros(nf, np.uint64), np.zeros(nf, np.int32), np.zeros(nf, np.uint64), np.zeros(nf, np.uint64),
                  np.zeros(nf, np.int32)] for _ in range(nbuf)]
-        pipe = C.c_void_p()
-        hc_b200.check(L.hc_pipeline_create(C.byref(pipe), local, 2), "hc_pipeline_create", L)
+        hc_b200.check(L.hc_pipeline_create(C.byref(pipe), local, depth), "hc_pipeline_create", L)
 
         def sub_c(k):
             o_off, o_len, o_st = tabs[k][:3]
@@ -515,22 +516,24 @@ def run_ours(args):
             return t
 
         def run_host(k_steps):
-            # step s: compress, then decompress of its output.  Compress jobs land on one pipeline slot, decompress jobs
-            # on the other (tickets alternate), so the decompress of step s overlaps the compress of step s+1; a host
-            # buffer is reused only after the decompress that read it has finished (three buffer sets).
-            tc = sub_c(0)
-            td = {}
+            # step s: compress, then decompress of its output.  Tickets alternate compress / decompress so that the two
+            # kinds land on different pipeline slots; up to depth/2 steps are in flight, a host buffer set is reused only
+            # after the decompress that read it has finished.
+            ahead = depth // 2
+            tc, td = {}, {}
+            nxt = 0                                           # next step whose compress is to be submitted
             for s in range(k_steps):
-                hc_b200.check(L.hc_pipeline_wait(pipe, tc), "compress job", L)
+                while nxt < k_steps and nxt < s + ahead:
+                    if nxt - nbuf in td:
+                        hc_b200.check(L.hc_pipeline_wait(pipe, td.pop(nxt - nbuf)), "decompress job", L)
+                    tc[nxt] = sub_c(nxt % nbuf)
+                    nxt += 1
+                hc_b200.check(L.hc_pipeline_wait(pipe, tc.pop(s)), "compress job", L)
                 td[s] = sub_d(s % nbuf)
-                if s + 1 < k_steps:
-                    if s + 1 - nbuf in td:
-                        hc_b200.check(L.hc_pipeline_wait(pipe, td.pop(s + 1 - nbuf)), "decompress job", L)
-                    tc = sub_c((s + 1) % nbuf)
             for s in sorted(td):
                 hc_b200.check(L.hc_pipeline_wait(pipe, td[s]), "decompress job", L)
 
-        run_host(3)                                               # warm-up: buffers of both slots allocated, every host buffer used
+        run_host(nbuf + 1)                                        # warm-up: the buffers of every slot allocated, every host buffer set used
         for k in range(nbuf):
             assert not tabs[k][2].any() and not tabs[k][5].any()
             assert np.array_equal(pin_dec[k].numpy()[: nf * FB].reshape(nf, FB), host_batch), "e2e round trip differs"
@@ -548,7 +551,7 @@ def run_ours(args):
         e2e = {"value": 2.0 * total_in / th / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(nf * FB + comp_bytes), "d2h_bytes_per_step": int(comp_bytes + nf * FB), "steps": args.steps,
                "ms_per_step": th * 1e3, "timer": "host wall clock around %d steps through hc_pipeline_submit_compress/_decompress + hc_pipeline_wait "
-               "(depth 2: the copies and kernels of neighbouring steps overlap), max over ranks" % args.steps}
+               "(depth %d: the copies and kernels of neighbouring steps overlap), max over ranks" % (args.steps, depth)}
 
     if rank != 0:
         if comm:
@@ -679,7 +682,8 @@ def main():
     ap.add_argument("--workload", default="c3ma", choices=sorted(WORKLOADS))
     ap.add_argument("--files", type=int, default=None, help="files per GPU (weak scaling; default: the workload's batch)")
     ap.add_argument("--total-files", type=int, default=None, help="strong scaling: this many files in total, cut over the ranks")
-    ap.add_argument("--overlap", type=int, default=2, help="codec streams that consecutive steps alternate between (1 = strictly one step at a time)")
+    ap.add_argument("--overlap", type=int, default=4, help="codec streams that consecutive steps alternate between (1 = strictly one step at a time, max 4)")
+    ap.add_argument("--depth", type=int, default=4, help="slots of the asynchronous host pipeline used by the e2e measurement (even: compress and decompress jobs alternate)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the -m sub-run and the saturated run")

@@ -384,12 +384,14 @@ static_assert(FGK_I_SC == (0x80000000u >> 13), "bit trick above");
 // The part of the update that is only entered when some level of the path ties with the node after it
 // (src/huffman.cpp:115-125: leader search, swap, continue from the leader's parent).  Same arguments
 // as fgk_update; `pre` holds this round's loads.
-HC_DEV void fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
+// Returns true if the path table may have changed (an internal node moved, or the walk left the table).
+HC_DEV bool fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
 {
     const u32 lanebits = (lane << 27) | FGK_I_TIE;
     u32 guard = 0;
+    bool changed = false;
     for (;;) {
-        if (++guard > 600u) { c.err = 1; return; }       // more rounds than nodes: never on a consistent tree
+        if (++guard > 600u) { c.err = 1; return true; }  // more rounds than nodes: never on a consistent tree
         const u32 depth = pf >> 12;
         const u32 W = pre.n.x;
         const bool tie = lane < depth && pre.n1.x == W;
@@ -442,11 +444,20 @@ HC_DEV void fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
                     sts32(c.rec + l, w + 1u);
                 }
             }
+            // the common outcome in one test: two leaves swapped, different parents, the leader is listed in the
+            // table and does not hang below the root (pfx 0x2000 .. 0x91ff)
+            if ((r & (FGK_I_NOSWAP | FGK_I_SAMEP | FGK_I_SC)) == 0u && pfl - 0x2000u < 0x7200u) {
+                pf = pfl - 0x1000u;
+                A = fgk_lookup(c, pf);
+                newpath = true;
+                break;
+            }
             if (r & FGK_I_NOSWAP) continue;
             if (r & FGK_I_SC) {
                 // the old node is level k0 of this path, the leader's path came with r
                 const u32 sh = FGK_D - 1u - k0;
                 c.lev = fgk_rebuild_pair_cold(c, ((k0 + 1u) << 12) | (((pf & 0x1ffu) >> sh) << sh), pfl, lane);
+                changed = true;
             } else if (r & FGK_I_SAMEP) {
                 continue;                                 // same parent: the levels above are as loaded
             }
@@ -454,7 +465,7 @@ HC_DEV void fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
                 // the leader lies deeper than the table: finish sequentially from its parent
                 const u32 pl = shfl(fgk_parent(yl), (int)k0);
                 c = fgk_update_seq(c, pl, lane);
-                return;
+                return true;
             }
             if ((pfl >> 12) == 1u) { hi = 0; break; }     // the leader hangs below the root: done
             pf = pfl - 0x1000u;                           // the parent of the leader: one level up, same path bits
@@ -465,7 +476,7 @@ HC_DEV void fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
         if (!newpath) {
             sts32_if(lane < hi, c.rec + A, W + 1u);
             syncwarp();
-            return;
+            return changed;
         }
         pre = fgk_preload(c, A);
     }
@@ -474,7 +485,9 @@ HC_DEV void fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
 // FGK update of a node whose path is in the table (src/huffman.cpp:113-127).  A = this lane's node
 // (fgk_lookup of pf), pf = depth << 12 | left-aligned path of the node the update starts from, `pre` =
 // fgk_preload(A).  Most symbols take the first exit: no level ties, every lane adds 1 to its node.
-HC_DEV void fgk_update(FgkCtx &c, u32 A, u32 pf, u32 lane, const FgkPre &pre)
+// Returns 0 on that exit (nothing but weights changed), 1 if leaves may have moved, 3 if the path table may
+// have changed as well.
+HC_DEV u32 fgk_update(FgkCtx &c, u32 A, u32 pf, u32 lane, const FgkPre &pre)
 {
     const bool valid = lane < (pf >> 12);
     const bool tie = valid && pre.n1.x == pre.n.x;
@@ -483,9 +496,9 @@ HC_DEV void fgk_update(FgkCtx &c, u32 A, u32 pf, u32 lane, const FgkPre &pre)
     if (!some) {
         sts32_if(valid, c.rec + A, pre.n.x + 1u);
         syncwarp();
-        return;
+        return 0u;
     }
-    fgk_update_ties(c, A, pf, lane, pre);
+    return fgk_update_ties(c, A, pf, lane, pre) ? 3u : 1u;
 }
 
 #if defined(HC_EMU_DEBUG) || defined(HC_FGK_CHECK)
@@ -706,12 +719,20 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
         syncwarp();
         if (i0 + 128u < m) cnext = ldg32(src + (i0 + 128u) / 4u + lane);
         const u32 cnt = (m - i0) < 128u ? (m - i0) : 128u;
+        // Lookahead, valid by construction: the entry (spf) and the path nodes (A) of the NEXT symbol are fetched while
+        // this symbol is processed.  An update that took the first exit of fgk_update changed nothing but weights, so
+        // they are still right; after any other update they are simply fetched again.
+        u32 y = lds8(c.buf), yn = lds8(c.buf + 1u);
+        u32 sp = lds32(c.spf + 4u * y);
+        u32 A = fgk_lookup(c, sp >> 16);
         for (u32 g0 = 0; g0 < cnt; g0 += 32) {
             const u32 gcnt = (cnt - g0) < 32u ? (cnt - g0) : 32u;
             for (u32 j = 0; j < gcnt; j++) {
-                const u32 y = lds8(c.buf + g0 + j);
-                const u32 sp = lds32(c.spf + 4u * y);
+                const u32 ynn = lds8(c.buf + ((g0 + j + 2u) & 255u));     // (past the chunk: never used, see the re-fetch below)
+                u32 spn = lds32(c.spf + 4u * yn);
+                u32 An = fgk_lookup(c, spn >> 16);
                 const u32 pf = sp >> 16;
+                u32 dirty;
                 if (pf == FGK_NOPATH) {
                     // Not yet transmitted, or deeper than the table.  Encode precedes update (src/transform.cpp:372-375):
                     // the code is read off the tree first, by a parent chase; a new symbol sends the NYT code + 8 raw
@@ -729,17 +750,24 @@ fgk_encode_kernel(const u8 *HC_RESTRICT sym, const u64 *HC_RESTRICT sym_off, con
                         fgk_table_split(c, n, pn, lane);
                     }
                     c = fgk_update_seq(c, start, lane);
+                    dirty = 1;
                 } else {
                     // the code of a leaf is its path (encode precedes update, src/transform.cpp:372-375)
                     if (lane == j) code = pf;
-                    const u32 A = fgk_lookup(c, pf);
-                    fgk_update(c, A, pf, lane, fgk_preload(c, A));
+                    dirty = fgk_update(c, A, pf, lane, fgk_preload(c, A));
+                }
+                if (dirty) {
+                    spn = lds32(c.spf + 4u * yn);
+                    An = fgk_lookup(c, spn >> 16);
                 }
 #if defined(HC_EMU_DEBUG) || defined(HC_FGK_CHECK)
                 syncwarp();
                 if (!c.err && ballot(!fgk_validate(c, lane, i0 + g0 + j))) c.err = 2;
                 syncwarp();
 #endif
+                y = yn; yn = ynn;
+                sp = spn;
+                A = An;
             }
             bw_pack(c, bw, code, lane);
             code = 0;
@@ -882,40 +910,46 @@ fgk_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const
     }
     const u32 m = (u32)m64;
     u32 *dst = (u32 *)(sym + sym_off[f]);
-    const u32 shd = 31u - (lane < FGK_D ? lane : 0u);
+    // lanes 0..8 look up levels 1..9; the others read one of the two pad entries behind the table, which always say
+    // "no node" (the root, which is internal as soon as the first symbol has arrived)
+    const u32 shd = lane < FGK_D ? 31u - lane : 31u;
+    const u32 ptd = lane < FGK_D ? c.ptj : c.pt + 2u * FGK_PT_N;
     const u32 lanekey = lane << 16;
-    for (u32 i = 0; i < m; i++) {
-        // The path table resolves the next FGK_D code bits in one step: lane j looks up the node that
-        // the first j + 1 bits lead to; the shallowest leaf among them ends the code (REDUX.MIN over
-        // lane << 16 | symbol).  The loads of the update's first round ride on the same round of loads.
-        const u32 t = (u32)(br.win >> 32);
-        const u32 e = lane < FGK_D ? lds16(c.ptj + 2u * (t >> shd)) : FGK_ROOT_O;
-        const FgkPre pre = fgk_preload(c, e);
-        const u32 ka = fgk_down(pre.n.y);
-        const u32 r = reduce_min((e != FGK_ROOT_O && (ka & FGK_LEAF)) ? (lanekey | (ka & 0x1ffu)) : 0xffffffffu);
-        u32 y;
-        if (r == 0xffffffffu || (r & 0x100u)) {
-            y = fgk_decode_cold(c, br, lane);
-            if (c.err) break;
-        } else {
-            const u32 depth = (r >> 16) + 1u;
-            y = r & 0xffu;
-            br_skip(br, depth, lane);
-            fgk_update(c, e, (depth << 12) | (t >> 23), lane, pre);
+    u32 e = lds16(ptd + 2u * ((u32)(br.win >> 32) >> shd));
+    for (u32 i0 = 0; i0 < m; i0 += 128) {
+        const u32 cnt = (m - i0) < 128u ? (m - i0) : 128u;
+        for (u32 i = 0; i < cnt; i++) {
+            // The path table resolves the next FGK_D code bits in one step: lane j looks up the node that the first
+            // j + 1 bits lead to; the shallowest leaf among them ends the code (REDUX.MIN over lane << 16 | symbol).
+            // The loads of the update's first round ride on the same round of loads.  A lane without a node holds
+            // the root: a leaf only before the first symbol, which the cold path handles.
+            const u32 t = (u32)(br.win >> 32);
+            const FgkPre pre = fgk_preload(c, e);
+            const u32 r = reduce_min((i32)pre.n.y < 0 ? (lanekey | ((pre.n.y >> 16) & 0x1ffu)) : 0xffffffffu);
+            u32 y, dirty;
+            if (r == 0xffffffffu || (r & 0x100u)) {
+                y = fgk_decode_cold(c, br, lane);
+                if (c.err) { i0 = m; break; }
+                dirty = 3;
+            } else {
+                const u32 depth = (r >> 16) + 1u;
+                y = r & 0xffu;
+                br_skip(br, depth, lane);
+                // the next code starts here: its table lookup only depends on this symbol's update if that changes
+                // the shape of the tree
+                const u32 en = lds16(ptd + 2u * ((u32)(br.win >> 32) >> shd));
+                dirty = fgk_update(c, e, (depth << 12) | (t >> 23), lane, pre);
+                e = en;
+            }
+            if (dirty & 2u) e = lds16(ptd + 2u * ((u32)(br.win >> 32) >> shd));
+            if (lane == 0) sts8(c.buf + i, y);
         }
-        if (lane == 0) sts8(c.buf + (i & 127u), y);
-        if ((i & 127u) == 127u) {
-            syncwarp();
-            stg32_stream(dst + (i >> 7) * 32u + lane, lds32(c.buf + 4u * lane));
-            syncwarp();
-        }
+        syncwarp();
+        if (cnt == 128u) stg32_stream(dst + (i0 >> 2) + lane, lds32(c.buf + 4u * lane));
+        else if (lane < (cnt + 3u) / 4u) dst[(i0 >> 2) + lane] = lds32(c.buf + 4u * lane);    // the last, partial group
+        syncwarp();
     }
     const bool underrun = br_consumed(br) > n * 8u;
-    if (!underrun) {
-        u32 rem = m & 127u;                                // symbols in the last partial group
-        syncwarp();
-        if (rem && lane < (rem + 3u) / 4u) dst[(m >> 7) * 32u + lane] = lds32(c.buf + 4u * lane);
-    }
     if (lane == 0) { sym_len[f] = m64; status[f] = c.err ? 102 : (underrun ? 9 : 0); }
 }
 
