@@ -331,6 +331,10 @@ def run_ours(args):
     d_in_len = torch.full((nf,), FB, dtype=i64, device=dev)
     d_width = torch.full((nf,), side, dtype=i64, device=dev)
     n_arms = max(1, min(args.overlap, 4))
+    # keep the resident buffers of all streams (and, later, of the e2e pipeline slots) well inside the 180 GB of HBM
+    cap_est = FB + FB // 3 + FB // 8 + 8192
+    per_stream = nf * (cap_est * 17 // 8 + 5 * FB)
+    n_arms = max(1, min(n_arms, int(70e9 // max(per_stream, 1))))
     arms = [DeviceArm(torch, hc_b200, L, dev, d_in, d_in_off, d_in_len, d_width, nf, FB, use_adapt) for _ in range(n_arms)]
     A0 = arms[0]
     for arm in arms:                                                  # per stream: scratch + result of the size exchange
@@ -492,7 +496,7 @@ def run_ours(args):
         lens_h = np.full(nf, FB, np.uint64)
         widths = np.full(nf, side, np.uint64)
         pipe = C.c_void_p()
-        depth = max(2, min(args.depth, 8)) & ~1
+        depth = max(2, min(args.depth, 8, int(60e9 // max(per_stream, 1)))) & ~1
         nbuf = depth + 1
         pin_cmp = [torch.empty(out_bytes + 16 * nf + 4096, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
         pin_dec = [torch.empty(nf * FB + 4096, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
