@@ -420,7 +420,7 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
     const u64 lbytes = ad_large_bytes(nf, max_out_len), tstride = lbytes ? adl_tmp_stride(max_out_len) : 0;
     u8 *ltmp = (u8 *)ws;
     ws = ws ? (void *)((u8 *)ws + lbytes) : ws;
-    HC_LAUNCH(adapt_index_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out_cap, out != nullptr,
+    HC_LAUNCH(adapt_index_kernel, dim3(file_grid(nf)), dim3(AD_IDX_WARPS * 32), 0, stream, in, in_off, in_len, out_cap, out != nullptr,
               (u32 *)ws, bs, out_len, status, nf);
     HC_CHECK_LAUNCH();
     if (!out) return 0;

@@ -87,3 +87,62 @@ def test_sharded_batch_equals_single_gpu(world, oracle):
         assert sizes == ref_sizes and offs == ref_off.tolist() and total == ref_total, rank
         blob += outs
     assert len(blob) == NFILES and all(a == o.tobytes() for a, o in zip(blob, one))
+
+
+def _lpt_worker(rank, world, port, q):
+    import hc_b200
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    side, n = 64, 22
+    # class-sorted batch: the contiguous split puts every high-entropy file on the first rank
+    kinds = ["random"] * 6 + ["walk"] * 5 + ["smooth"] * 6 + ["const"] * 5
+    files = [synth.image(kinds[i], side, 8000 + i).reshape(-1) for i in range(n)]
+    lo, hi = shard.shard_range(n, rank, world)
+    d_in = torch.from_numpy(np.stack(files[lo:hi])).cuda()
+    sc = shard.ShardedCompressor(hc_b200.lib(), rank, world, torch.device("cuda", rank), side, use_adapt=True)
+    res = {}
+    for policy in ("contiguous", "lpt"):
+        r = sc.compress(d_in, lo, n, policy)
+        torch.cuda.synchronize()
+        lens = r["out_len"].cpu().tolist()
+        offs = r["out_off"].cpu().tolist()
+        blob = r["out"].cpu().numpy()
+        res[policy] = {"ids": r["ids"], "bytes": [blob[o:o + ln].tobytes() for o, ln in zip(offs, lens)], "sizes": r["sizes"].cpu().tolist(),
+                       "offsets": r["offsets"].cpu().tolist(), "load": r["load"]}
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cost_aware_sharding_gives_identical_files(world, oracle):
+    """LPT placement of the FGK stage + migration of the symbol streams over NVLink: same bytes, same offsets table,
+    better balance than contiguous slices on a class-sorted batch."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    side, n = 64, 22
+    kinds = ["random"] * 6 + ["walk"] * 5 + ["smooth"] * 6 + ["const"] * 5
+    files = [synth.image(kinds[i], side, 8000 + i).reshape(-1) for i in range(n)]
+    exp = [oracle.compress(f, diff=True, adapt=True, width=side)[1].tobytes() for f in files]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lpt_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for policy in ("contiguous", "lpt"):
+        seen = {}
+        for rank in range(world):
+            r = res[rank][policy]
+            assert r["sizes"] == [len(e) for e in exp], (policy, rank)
+            for g, b in zip(r["ids"], r["bytes"]):
+                assert g not in seen
+                seen[g] = b
+        assert sorted(seen) == list(range(n)) and all(seen[g] == exp[g] for g in range(n)), policy
+    lc, ll = res[0]["contiguous"]["load"], res[0]["lpt"]["load"]
+    assert max(ll) < max(lc) and max(ll) <= 4 / 3 * max(sum(ll) / world, max(len(e) for e in exp) * 8)

@@ -79,3 +79,47 @@ def test_size_allgather_matches_single_process():
         for rank, sizes, off, total in _run(world, nfiles):
             assert sizes == ref_sizes, (world, rank)
             assert off == ref_off.tolist() and total == ref_total
+
+
+def test_lpt_assignment_balances_and_is_deterministic():
+    rng = np.random.default_rng(3)
+    costs = list(rng.integers(1, 1000, 57)) + [100000, 90000]
+    for world in (1, 2, 3, 8):
+        owner, load = shard.lpt_assign(costs, world)
+        assert owner == shard.lpt_assign(list(costs), world)[0]
+        assert sorted(set(owner)) == list(range(world)) and sum(load) == sum(costs)
+        # LPT is within 4/3 of the optimum, which is at least max(largest job, mean load)
+        assert max(load) <= 4 / 3 * max(max(costs), sum(costs) / world) + 1
+    # the two giants never share a rank when there is a choice; a class-sorted batch is spread evenly
+    owner, _ = shard.lpt_assign(costs, 2)
+    assert owner[-1] != owner[-2]
+    sorted_costs = [262144] * 16 + [1000] * 48
+    _, load = shard.lpt_assign(sorted_costs, 4)
+    assert max(load) - min(load) <= 1000
+    cont = shard.contiguous_assign(64, 4)
+    assert sum(c for c, r in zip(sorted_costs, cont) if r == 0) == 16 * 262144
+
+
+def _xchg_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    parts = [torch.full((100 * rank + 10 * d + 1,), 16 * rank + d, dtype=torch.uint8) for d in range(world)]
+    got = shard.exchange_streams(parts)
+    q.put((rank, [(int(t.numel()), int(t[0]) if t.numel() else -1) for t in got]))
+    dist.destroy_process_group()
+
+
+def test_stream_exchange_gloo():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_xchg_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        assert res[rank] == [(100 * s + 10 * rank + 1, 16 * s + rank) for s in range(world)]
