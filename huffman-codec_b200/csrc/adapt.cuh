@@ -383,18 +383,144 @@ HC_DEV AdaptHeader ad_parse_header(const u8 *src, u64 m)
 
 constexpr i32 AD_ST_SERIAL = 102;   // internal: block table too small, use the serial decoder
 
+// Which of the two index kernels walks a file: big matrices with big blocks (the 4096 x 4096 images of BASELINE
+// config 4: one block holds up to a million tokens) go to the CTA-wide kernel, everything else -- blocks of a few
+// dozen tokens, where a step ends at the first block boundary whatever its width -- to the one-warp kernel
+// (measured on the 512 x 512 batch: one warp 6.2 ms, eight cooperating warps 37 ms).
+HC_DEV bool ad_index_wide(const AdaptHeader &hd, u64 wide_min) { return hd.b >= 64u && hd.total >= wide_min; }
+
+HC_KERNEL HC_LAUNCH_BOUNDS(32, 1)
+adapt_index_warp_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
+                   const u64 *HC_RESTRICT out_cap, bool have_out, u32 *HC_RESTRICT blk_start, u64 blk_stride,
+                   u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf, u64 wide_min)
+{
+    const u32 f = blockIdx.x, lane = threadIdx.x & 31u;
+    if (f >= nf) return;
+    const u64 m = in_len[f];
+    const u8 *src = in + in_off[f];
+    const AdaptHeader hd = ad_parse_header(src, m);
+    if (hd.status) { if (lane == 0) { out_len[f] = 0; status[f] = hd.status; } return; }
+    if (ad_index_wide(hd, wide_min)) return;           // walked by adapt_index_cta_kernel
+    // A token yields at most 255 bytes, so a header that promises more than 255 bytes per payload byte
+    // cannot be satisfied (a crafted w = h = 2^31 header would otherwise make the caller size its output
+    // for 2^62 bytes): such a stream is only walked for its exact error (13 or 14), nothing is sized or written.
+    const bool hopeless = hd.total > 255u * (m - 24u - hd.dir_bytes);
+    if (!have_out && !hopeless) { if (lane == 0) { out_len[f] = hd.total; status[f] = 0; } return; }
+    if (!hopeless) {
+        if (hd.total > out_cap[f]) { if (lane == 0) { out_len[f] = hd.total; status[f] = 100; } return; }
+        if (hd.nb + 1 > blk_stride || m > 0xfffffff0ull) { if (lane == 0) { out_len[f] = hd.total; status[f] = AD_ST_SERIAL; } return; }
+    }
+    u32 *tab = hopeless ? nullptr : blk_start + (u64)f * blk_stride;
+    u64 pos = 24 + hd.dir_bytes;
+    i32 err = 0;
+    u64 blk = 0;
+    // (crafted headers: block sides beyond 32 bits saturate the block size, offsets that would wrap end the loops)
+    for (u64 by = 0; by < hd.h && !err; by = by + hd.b < by ? hd.h : by + hd.b) {
+        const u64 bh = hd.h - by < hd.b ? hd.h - by : hd.b;
+        for (u64 bx = 0; bx < hd.w && !err; bx = bx + hd.b < bx ? hd.w : bx + hd.b, blk++) {
+            const u64 bw = hd.w - bx < hd.b ? hd.w - bx : hd.b;
+            const u64 req = (bw >> 32 || bh >> 32) ? ~0ull : bw * bh;
+            if (lane == 0 && tab) tab[blk] = (u32)pos;
+            u64 produced = 0;
+            u32 state = 0, prev_last = 0;
+            while (produced < req) {
+                // 128 tokens per step: 4 consecutive bytes per lane
+                const u64 idx = pos + 4u * lane;
+                u32 b[4], nv = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const bool v = idx + k < m;
+                    b[k] = v ? src[idx + k] : 0u;
+                    nv += v ? 1u : 0u;
+                }
+                u32 pb = shfl_up(b[3], 1);
+                if (lane == 0) pb = prev_last;
+                // decoder state map of the lane's (valid) bytes
+                u32 map = MAP_ID, pr = pb;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if ((u32)k < nv) map = map_compose(map, b[k] == pr ? MAP_EQ : MAP_NE);
+                    pr = b[k];
+                }
+                u32 inc = map;
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 t = shfl_up(inc, d);
+                    if (lane >= (u32)d) inc = map_compose(t, inc);
+                }
+                u32 exm = shfl_up(inc, 1);
+                if (lane == 0) exm = MAP_ID;
+                // output length of each of the lane's tokens
+                u32 s = map_apply(exm, state), len[4], sum = 0;
+                pr = pb;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    len[k] = 0;
+                    if ((u32)k < nv) {
+                        if (s == 3u) { len[k] = b[k]; s = 0; }
+                        else { len[k] = 1; s = (s == 0u) ? 1u : (b[k] == pr ? s + 1u : 1u); }
+                    }
+                    pr = b[k];
+                    sum += len[k];
+                }
+                u32 cum = sum;
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 t = shfl_up(cum, d);
+                    if (lane >= (u32)d) cum += t;
+                }
+                const u64 rem = req - produced;
+                const u32 hit = ballot(nv != 0u && (u64)cum >= rem);
+                if (hit == 0u) {
+                    // the step did not complete the block: consume every valid token
+                    u32 tv = nv;
+                    for (int d = 16; d > 0; d >>= 1) tv += shfl_xor(tv, d);
+                    if (tv == 0u) { err = 14; break; }                  // src/transform.cpp:170-174
+                    produced += shfl(cum, 31);
+                    state = map_apply(shfl(inc, 31), state);
+                    const u32 last_lane = (tv - 1u) >> 2;
+                    {
+                        // byte value of the last consumed token (lane last_lane, slot (tv-1)&3)
+                        const u32 slot = (tv - 1u) & 3u;
+                        const u32 mine = slot == 0 ? b[0] : slot == 1 ? b[1] : slot == 2 ? b[2] : b[3];
+                        prev_last = shfl(mine, (int)last_lane);
+                    }
+                    pos += tv;
+                    if (tv < 128u && produced < req) { err = 14; break; }
+                } else {
+                    // the block ends inside lane `hl`: find the token
+                    const int hl = ffs(hit) - 1;
+                    const u32 before = shfl(cum - sum, hl);               // produced by the lanes before hl
+                    const u32 l0 = shfl(len[0], hl), l1 = shfl(len[1], hl), l2 = shfl(len[2], hl), l3 = shfl(len[3], hl);
+                    const u64 need = rem - before;                        // still missing when lane hl starts (>= 1)
+                    u32 tok, got;
+                    if ((u64)l0 >= need) { tok = 0; got = l0; }
+                    else if ((u64)l0 + l1 >= need) { tok = 1; got = l0 + l1; }
+                    else if ((u64)l0 + l1 + l2 >= need) { tok = 2; got = l0 + l1 + l2; }
+                    else { tok = 3; got = l0 + l1 + l2 + l3; }
+                    if ((u64)got > need) { err = 13; break; }            // src/transform.cpp:180-184
+                    pos += 4u * (u32)hl + tok + 1u;
+                    produced = req;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        if (tab) tab[hd.nb] = (u32)pos;
+        out_len[f] = hopeless ? 0 : hd.total;
+        status[f] = err ? err : (pos != m ? 15 : 0);                    // src/transform.cpp:354-358
+    }
+}
+
 constexpr u32 AD_IDX_WARPS = 8;          // warps of a CTA that walk one file's token stream together
 
 // One CTA per file.  A step covers 8 x 128 tokens: every warp takes 128 consecutive tokens (4 per lane),
 // scans its decoder state maps and token lengths with shuffles, the per-warp totals are combined through
 // shared memory, and the first token that completes the current block ends the step there (the decoder
-// state resets at a block boundary, so nothing behind it can be classified yet).  Small blocks (B = 8)
-// therefore advance one block per step as before; a 1024 x 1024 block of a 4096 x 4096 image advances
-// 1024 tokens per step instead of 128.
+// state resets at a block boundary, so nothing behind it can be classified yet).  A 1024 x 1024 block of a
+// 4096 x 4096 image advances 1024 tokens per step instead of 128.
 HC_KERNEL HC_LAUNCH_BOUNDS(AD_IDX_WARPS * 32, 1)
-adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
-                   const u64 *HC_RESTRICT out_cap, bool have_out, u32 *HC_RESTRICT blk_start, u64 blk_stride,
-                   u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
+adapt_index_cta_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
+                       const u64 *HC_RESTRICT out_cap, bool have_out, u32 *HC_RESTRICT blk_start, u64 blk_stride,
+                       u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf, u64 wide_min)
 {
     HC_SHARED u32 s_map[2][AD_IDX_WARPS], s_sum[2][AD_IDX_WARPS], s_tv[2][AD_IDX_WARPS], s_last[2][AD_IDX_WARPS], s_hit[2][AD_IDX_WARPS];
     const u32 f = blockIdx.x, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -402,7 +528,7 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
     const u64 m = in_len[f];
     const u8 *src = in + in_off[f];
     const AdaptHeader hd = ad_parse_header(src, m);
-    if (hd.status) { if (threadIdx.x == 0) { out_len[f] = 0; status[f] = hd.status; } return; }
+    if (hd.status || !ad_index_wide(hd, wide_min)) return;   // walked (or rejected) by adapt_index_warp_kernel
     // A token yields at most 255 bytes, so a header that promises more than 255 bytes per payload byte
     // cannot be satisfied (a crafted w = h = 2^31 header would otherwise make the caller size its output
     // for 2^62 bytes): such a stream is only walked for its exact error (13 or 14), nothing is sized or written.
@@ -413,6 +539,8 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
         if (hd.nb + 1 > blk_stride || m > 0xfffffff0ull) { if (threadIdx.x == 0) { out_len[f] = hd.total; status[f] = AD_ST_SERIAL; } return; }
     }
     u32 *tab = hopeless ? nullptr : blk_start + (u64)f * blk_stride;
+    const u32 nw = AD_IDX_WARPS;
+#define AD_IDX_SYNC() syncthreads()
     u64 pos = 24 + hd.dir_bytes;
     i32 err = 0;
     u64 blk = 0;
@@ -455,7 +583,7 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
                 // entry state of this warp = the maps of the warps before it applied to the step's entry state;
                 // the token lengths need it, so the maps are exchanged first
                 if (lane == 31) s_map[par][wid] = inc;
-                syncthreads();
+                AD_IDX_SYNC();
                 u32 wstate = state;
                 for (u32 w = 0; w < wid; w++) wstate = map_apply(s_map[par][w], wstate);
                 // output length of each of the lane's tokens
@@ -486,22 +614,22 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
                     const u32 lastv = shfl(mine, (int)((tv ? tv - 1u : 0u) >> 2));
                     if (lane == 0) s_last[par][wid] = lastv;
                 }
-                syncthreads();
+                AD_IDX_SYNC();
                 u64 before_w = 0;                 // bytes produced by the warps before this one
                 for (u32 w = 0; w < wid; w++) before_w += s_sum[par][w];
                 const u64 rem = req - produced;
                 const u32 hit = before_w < rem ? ballot(nv != 0u && before_w + (u64)cum >= rem) : 0u;
                 if (lane == 0) s_hit[par][wid] = hit;
-                syncthreads();
-                u32 hw = AD_IDX_WARPS;            // first warp in which the block ends
-                for (u32 w = 0; w < AD_IDX_WARPS; w++)
-                    if (s_hit[par][w] && hw == AD_IDX_WARPS) hw = w;
-                if (hw == AD_IDX_WARPS) {
+                AD_IDX_SYNC();
+                u32 hw = nw;                      // first warp in which the block ends
+                for (u32 w = 0; w < nw; w++)
+                    if (s_hit[par][w] && hw == nw) hw = w;
+                if (hw == nw) {
                     // the step did not complete the block: consume every valid token of all warps
                     u32 tvall = 0;
                     u64 sumall = 0;
                     u32 st = state, lastv = prev_last;
-                    for (u32 w = 0; w < AD_IDX_WARPS; w++) {
+                    for (u32 w = 0; w < nw; w++) {
                         if (s_tv[par][w]) lastv = s_last[par][w];
                         tvall += s_tv[par][w];
                         sumall += s_sum[par][w];
@@ -512,7 +640,7 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
                     state = st;
                     prev_last = lastv;
                     pos += tvall;
-                    if (tvall < 128u * AD_IDX_WARPS && produced < req) { err = 14; break; }
+                    if (tvall < 128u * nw && produced < req) { err = 14; break; }
                 } else {
                     // the block ends inside warp hw, lane hl: that warp finds the token and publishes the result
                     if (wid == hw) {
@@ -530,11 +658,11 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
                             s_tv[par ^ 1u][0] = 128u * hw + 4u * (u32)hl + tok + 1u;      // tokens consumed by the block's end
                         }
                     }
-                    syncthreads();
+                    AD_IDX_SYNC();
                     if (s_sum[par ^ 1u][0]) { err = 13; break; }
                     pos += s_tv[par ^ 1u][0];
                     produced = req;
-                    syncthreads();                // the scratch words are reused by the next step's exchange
+                    AD_IDX_SYNC();                // the scratch words are reused by the next step's exchange
                 }
                 par ^= 1u;
             }
@@ -545,6 +673,7 @@ adapt_index_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, cons
         out_len[f] = hopeless ? 0 : hd.total;
         status[f] = err ? err : (pos != m ? 15 : 0);                    // src/transform.cpp:354-358
     }
+#undef AD_IDX_SYNC
 }
 
 constexpr int AD_EXP_TPB = 256;

@@ -420,9 +420,18 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
     const u64 lbytes = ad_large_bytes(nf, max_out_len), tstride = lbytes ? adl_tmp_stride(max_out_len) : 0;
     u8 *ltmp = (u8 *)ws;
     ws = ws ? (void *)((u8 *)ws + lbytes) : ws;
-    HC_LAUNCH(adapt_index_kernel, dim3(file_grid(nf)), dim3(AD_IDX_WARPS * 32), 0, stream, in, in_off, in_len, out_cap, out != nullptr,
-              (u32 *)ws, bs, out_len, status, nf);
+    // matrices of at least this many bytes (with blocks of 64 and more) are indexed by the CTA-wide kernel
+    // (HC_INDEX_WIDE_MIN: test hook, so that the CPU suite reaches that kernel with small images)
+    static const u64 wide_min = getenv("HC_INDEX_WIDE_MIN") ? strtoull(getenv("HC_INDEX_WIDE_MIN"), nullptr, 10) : (u64)(4u << 20);
+    HC_LAUNCH(adapt_index_warp_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out_cap, out != nullptr,
+              (u32 *)ws, bs, out_len, status, nf, wide_min);
     HC_CHECK_LAUNCH();
+    if (max_out_len >= wide_min || !out) {
+        // big matrices with big blocks: eight warps per file walk the token stream together
+        HC_LAUNCH(adapt_index_cta_kernel, dim3(file_grid(nf)), dim3(AD_IDX_WARPS * 32), 0, stream, in, in_off, in_len, out_cap,
+                  out != nullptr, (u32 *)ws, bs, out_len, status, nf, wide_min);
+        HC_CHECK_LAUNCH();
+    }
     if (!out) return 0;
     u64 chunks = max_out_len / (64 * 1024);
     if (chunks < 1) chunks = 1;

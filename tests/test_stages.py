@@ -446,3 +446,18 @@ def test_fgk_stress_roundtrip(be, oracle):
     assert not be.download(st2, src.nf * 4, np.int32).any()
     for i, (f, g) in enumerate(zip(files, dst.files(dst.lens()))):
         assert np.array_equal(g, f), (i, f.size)
+
+
+def test_adapt_index_cta_kernel_on_emulator():
+    """The CTA-wide block index kernel only takes matrices of 4 MiB and more (BASELINE config 4); the library's test
+    hook HC_INDEX_WIDE_MIN lowers that bound so that the CPU suite reaches it with small images (the threshold is
+    read once per process, hence the child process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HC_INDEX_WIDE_MIN="1024")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider", "-m", "not gpu",
+                        "-k", "(adapt_decode or adapt_decode_errors) and emu"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout
