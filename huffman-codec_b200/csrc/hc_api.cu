@@ -44,6 +44,14 @@ void hc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
         if (e_ != cudaSuccess) return -(int)e_;            \
     } while (0)
 #define HC_CHECK_LAUNCH() HC_CUDA(cudaGetLastError())
+#define HC_TRY(x)                  \
+    do {                           \
+        int r_ = (x);              \
+        if (r_ != 0) return r_;    \
+    } while (0)
+#ifndef HC_ADAPT_GROUP_DEFAULT_MB
+#define HC_ADAPT_GROUP_DEFAULT_MB 0
+#endif
 
 namespace hcd {
 
@@ -111,6 +119,8 @@ HC_KERNEL compress_prep_kernel(const u64 *HC_RESTRICT len, const u64 *HC_RESTRIC
         if (w == 0 || n % w != 0) { s = 6; w = 0; }
         else h = n / w;
     }
+    // the transform kernels keep per-file positions in 32 bits: a file of 2 GiB or more is refused, not mangled
+    if (!s && n >= (1ull << 31)) s = 100;
     w_eff[i] = w; h_eff[i] = h;
     len_eff[i] = s ? 0 : n;
     flags[i] = (u8)(((use_diff ? 1 : 0) << 7) | ((use_adapt ? 1 : 0) << 6));
@@ -323,19 +333,12 @@ extern "C" uint64_t hc_adapt_encode_ws_bytes(uint32_t nf, uint64_t max_len)
     return ad_large_bytes(nf, max_len) + (uint64_t)nf * ((ad_cost_stride(max_len) + ad_off_stride(max_len)) * 4 + 8) + 256;
 }
 
-extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
-                                     const uint64_t *width, const uint64_t *height,
-                                     uint8_t *out, const uint64_t *out_off, uint64_t *out_len,
-                                     uint64_t *chosen_b, int32_t *status,
-                                     uint32_t nf, uint64_t max_len, void *ws, hc_stream_t stream)
+// the adaptive encoder for files [0, nf) of the arrays it is given (the caller passes pointers to a group's first file)
+static int adapt_encode_range(const uint8_t *in, const uint64_t *in_off, const uint64_t *width, const uint64_t *height,
+                              uint8_t *out, const uint64_t *out_off, uint64_t *out_len, int32_t *status,
+                              uint32_t nf, uint64_t max_len, u8 *ltmp, u64 lbytes, u64 tstride, u32 *cost, u64 cs, u32 *boff, u64 os,
+                              u64 *cb, hc_stream_t stream)
 {
-    if (nf == 0) return 0;
-    const u64 cs = ad_cost_stride(max_len), os = ad_off_stride(max_len);
-    const u64 lbytes = ad_large_bytes(nf, max_len), tstride = lbytes ? adl_tmp_stride(max_len) : 0;
-    u8 *ltmp = (u8 *)ws;
-    u32 *cost = (u32 *)((u8 *)ws + lbytes);
-    u32 *boff = cost + (u64)nf * cs;
-    u64 *cb = (u64 *)(((uintptr_t)(boff + (u64)nf * os) + 7) & ~(uintptr_t)7);
     // work split: enough CTAs to fill 148 SMs, at most one chunk per 64 KiB of image
     u64 chunks = max_len / (64 * 1024);
     if (chunks < 1) chunks = 1;
@@ -388,6 +391,45 @@ extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
                   (const u32 *)cost, cs, (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status);
         HC_CHECK_LAUNCH();
     }
+    return 0;
+}
+
+// L2-sized groups: the search kernel reads every pixel once and the emit kernels read them again; when the files of a
+// group (and the streams they produce) fit the 126 MB L2 together, the second read does not go to HBM.  group_bytes = 0:
+// the whole batch in one pass.
+static u32 adapt_group_files(u32 nf, u64 bytes_per_file)
+{
+    // HC_ADAPT_GROUP_FILES / HC_ADAPT_GROUP_MB: experiment and test hooks
+    static const u64 files = getenv("HC_ADAPT_GROUP_FILES") ? strtoull(getenv("HC_ADAPT_GROUP_FILES"), nullptr, 10) : 0;
+    static const u64 bytes = getenv("HC_ADAPT_GROUP_MB") ? strtoull(getenv("HC_ADAPT_GROUP_MB"), nullptr, 10) << 20 : (u64)HC_ADAPT_GROUP_DEFAULT_MB << 20;
+    u64 g = nf;
+    if (files) g = files;
+    else if (bytes && bytes_per_file) {
+        g = bytes / bytes_per_file;
+        if (g < 296) g = 296;                             // never fewer than two files per SM
+    }
+    return (u32)(g < 1 ? 1 : (g > nf ? nf : g));
+}
+
+extern "C" int hc_adapt_encode_batch(const uint8_t *in, const uint64_t *in_off,
+                                     const uint64_t *width, const uint64_t *height,
+                                     uint8_t *out, const uint64_t *out_off, uint64_t *out_len,
+                                     uint64_t *chosen_b, int32_t *status,
+                                     uint32_t nf, uint64_t max_len, void *ws, hc_stream_t stream)
+{
+    if (nf == 0) return 0;
+    const u64 cs = ad_cost_stride(max_len), os = ad_off_stride(max_len);
+    const u64 lbytes = ad_large_bytes(nf, max_len), tstride = lbytes ? adl_tmp_stride(max_len) : 0;
+    u8 *ltmp = (u8 *)ws;
+    u32 *cost = (u32 *)((u8 *)ws + lbytes);
+    u32 *boff = cost + (u64)nf * cs;
+    u64 *cb = (u64 *)(((uintptr_t)(boff + (u64)nf * os) + 7) & ~(uintptr_t)7);
+    const u32 group = adapt_group_files(nf, max_len);
+    for (u32 f0 = 0; f0 < nf; f0 += group) {
+        const u32 n = nf - f0 < group ? nf - f0 : group;
+        HC_TRY(adapt_encode_range(in, in_off + f0, width + f0, height + f0, out, out_off + f0, out_len + f0, status + f0, n, max_len,
+                                  ltmp + (u64)f0 * tstride, lbytes, tstride, cost + (u64)f0 * cs, cs, boff + (u64)f0 * os, os, cb + f0, stream));
+    }
     if (chosen_b)
         HC_CUDA(cudaMemcpyAsync(chosen_b, cb, (size_t)nf * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
@@ -401,37 +443,23 @@ extern "C" uint64_t hc_adapt_decode_ws_bytes(uint32_t nf, uint64_t max_out_len)
     return ad_large_bytes(nf, max_out_len) + (uint64_t)nf * ad_blk_stride(max_out_len) * 4 + 256;
 }
 
-extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
-                                     uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
-                                     uint64_t *out_len, int32_t *status,
-                                     uint32_t nf, uint64_t max_in_len, uint64_t max_out_len,
-                                     void *ws, hc_stream_t stream)
+// the adaptive decoder for files [0, nf) of the arrays it is given; ws = this group's block table
+static int adapt_decode_range(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                              uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
+                              uint64_t *out_len, int32_t *status, uint32_t nf, uint64_t max_out_len,
+                              u8 *ltmp, u64 lbytes, u64 tstride, void *ws, u64 bs, hc_stream_t stream)
 {
-    (void)max_in_len;
-    if (nf == 0) return 0;
-    if (out && !ws) {
-        // no scratch: one thread per file (slow, kept for callers that cannot provide ws)
-        HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off,
-                  out_cap, out_len, status, nf, (i32)-1);
-        HC_CHECK_LAUNCH();
-        return 0;
-    }
-    const u64 bs = ad_blk_stride(max_out_len);
-    const u64 lbytes = ad_large_bytes(nf, max_out_len), tstride = lbytes ? adl_tmp_stride(max_out_len) : 0;
-    u8 *ltmp = (u8 *)ws;
-    ws = ws ? (void *)((u8 *)ws + lbytes) : ws;
     // matrices of at least this many bytes (with blocks of 64 and more) are indexed by the CTA-wide kernel
     // (HC_INDEX_WIDE_MIN: test hook, so that the CPU suite reaches that kernel with small images)
     static const u64 wide_min = getenv("HC_INDEX_WIDE_MIN") ? strtoull(getenv("HC_INDEX_WIDE_MIN"), nullptr, 10) : (u64)(4u << 20);
     HC_LAUNCH(adapt_index_warp_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out_cap, out != nullptr,
               (u32 *)ws, bs, out_len, status, nf, wide_min);
     HC_CHECK_LAUNCH();
-    if (max_out_len >= wide_min || !out) {
-        // big matrices with big blocks: eight warps per file walk the token stream together
-        HC_LAUNCH(adapt_index_cta_kernel, dim3(file_grid(nf)), dim3(AD_IDX_WARPS * 32), 0, stream, in, in_off, in_len, out_cap,
-                  out != nullptr, (u32 *)ws, bs, out_len, status, nf, wide_min);
-        HC_CHECK_LAUNCH();
-    }
+    // big matrices with big blocks: eight warps per file walk the token stream together.  Always launched: which files
+    // are "big" is decided by their headers (a crafted header may claim anything), the others return at once
+    HC_LAUNCH(adapt_index_cta_kernel, dim3(file_grid(nf)), dim3(AD_IDX_WARPS * 32), 0, stream, in, in_off, in_len, out_cap,
+              out != nullptr, (u32 *)ws, bs, out_len, status, nf, wide_min);
+    HC_CHECK_LAUNCH();
     if (!out) return 0;
     u64 chunks = max_out_len / (64 * 1024);
     if (chunks < 1) chunks = 1;
@@ -466,6 +494,35 @@ extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, 
     HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off, out_cap,
               out_len, status, nf, (i32)AD_ST_SERIAL);
     HC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int hc_adapt_decode_batch(const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                                     uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
+                                     uint64_t *out_len, int32_t *status,
+                                     uint32_t nf, uint64_t max_in_len, uint64_t max_out_len,
+                                     void *ws, hc_stream_t stream)
+{
+    (void)max_in_len;
+    if (nf == 0) return 0;
+    if (out && !ws) {
+        // no scratch: one thread per file (slow, kept for callers that cannot provide ws)
+        HC_LAUNCH(adapt_decode_kernel, dim3(file_grid(nf)), dim3(32), 0, stream, in, in_off, in_len, out, out_off,
+                  out_cap, out_len, status, nf, (i32)-1);
+        HC_CHECK_LAUNCH();
+        return 0;
+    }
+    const u64 bs = ad_blk_stride(max_out_len);
+    const u64 lbytes = ad_large_bytes(nf, max_out_len), tstride = lbytes ? adl_tmp_stride(max_out_len) : 0;
+    u8 *ltmp = (u8 *)ws;
+    u32 *tab = ws ? (u32 *)((u8 *)ws + lbytes) : nullptr;
+    const u32 group = out ? adapt_group_files(nf, max_out_len) : nf;   // L2-sized groups: the index pass and the expansion read the same tokens
+    for (u32 f0 = 0; f0 < nf; f0 += group) {
+        const u32 n = nf - f0 < group ? nf - f0 : group;
+        HC_TRY(adapt_decode_range(in, in_off + f0, in_len + f0, out, out ? out_off + f0 : nullptr, out_cap ? out_cap + f0 : nullptr, out_len + f0,
+                                  status + f0, n, max_out_len, ltmp ? ltmp + (u64)f0 * tstride : nullptr, lbytes, tstride,
+                                  tab ? (void *)(tab + (u64)f0 * bs) : nullptr, bs, stream));
+    }
     return 0;
 }
 
@@ -590,11 +647,28 @@ struct hc_codec {
     std::vector<hc_codec *> kids;       // group pipelines of the host-level batch calls (own stream + buffers)
 };
 
-#define HC_TRY(x)                  \
-    do {                           \
-        int r_ = (x);              \
-        if (r_ != 0) return r_;    \
-    } while (0)
+// the entry points leave the caller's current device as they found it
+struct DevGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DevGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define HC_ON_DEVICE(dev)                                  \
+    DevGuard dev_guard_(dev);                              \
+    if (dev_guard_.err != cudaSuccess) return -(int)dev_guard_.err
+
+// on every exit of a host-level batch call (errors included) nothing of the call is in flight any more: the
+// asynchronous copies into the caller's buffers have completed or were never started
+struct KidsSync {
+    hc_codec *c;
+    explicit KidsSync(hc_codec *c_) : c(c_) {}
+    ~KidsSync();
+};
 
 static void stage_begin(hc_codec *c)
 {
@@ -609,12 +683,17 @@ static void stage_mark(hc_codec *c, const char *name)
     cudaEventRecord(c->ev[c->nstages], c->stream);
 }
 
+KidsSync::~KidsSync()
+{
+    for (hc_codec *k : c->kids) cudaStreamSynchronize(k->stream);
+}
+
 extern "C" int hc_codec_create(hc_codec **out, int device)
 {
     int n = hc_device_count();
     if (n < 0) return n;
     if (n == 0 || device >= n) return -100;     // cudaErrorNoDevice
-    HC_CUDA(cudaSetDevice(device));
+    HC_ON_DEVICE(device);
     hc_codec *c = new hc_codec();
     c->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -630,7 +709,7 @@ extern "C" void hc_codec_destroy(hc_codec *c)
     if (!c) return;
     for (hc_codec *k : c->kids) hc_codec_destroy(k);
     c->kids.clear();
-    cudaSetDevice(c->device);
+    DevGuard dev_guard_(c->device);
     cudaStreamSynchronize(c->stream);
     c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release(); c->ord.release(); c->jt.release();
     c->htab.release();
@@ -685,7 +764,7 @@ extern "C" int hc_compress_device(hc_codec *c, const uint8_t *d_in, const uint64
                                   uint64_t *d_out_len, int32_t *d_status)
 {
     if (nf == 0) return 0;
-    HC_CUDA(cudaSetDevice(c->device));
+    HC_ON_DEVICE(c->device);
     cudaStream_t s = c->stream;
     HC_TRY(c->tab.ensure((size_t)T_NSLOTS * nf * 8));
     TabView t{(u8 *)c->tab.p, nf};
@@ -804,7 +883,7 @@ extern "C" int hc_decompress_device(hc_codec *c, const uint8_t *d_in, const uint
                                     uint64_t *d_out_len, int32_t *d_status)
 {
     if (nf == 0) return 0;
-    HC_CUDA(cudaSetDevice(c->device));
+    HC_ON_DEVICE(c->device);
     if (kinds == 0) kinds = HC_KIND_PLAIN | HC_KIND_ADAPT | HC_KIND_DIFF;
     stage_begin(c);
     HC_TRY(dec_fgk(c, d_in, d_in_off, d_in_len, nf, max_sym_len));
@@ -895,9 +974,10 @@ extern "C" int hc_compress_batch(hc_codec *c,
                                  uint64_t *out_off, uint64_t *out_len, int32_t *status)
 {
     if (nf == 0) return 0;
-    HC_CUDA(cudaSetDevice(c->device));
+    HC_ON_DEVICE(c->device);
     const u32 ng = group_count(nf);
     HC_TRY(ensure_kids(c, ng));
+    KidsSync sync_on_exit(c);
     std::vector<GroupJob> jobs(ng);
     // phase 1: enqueue upload + the whole compression pipeline of every group
     for (u32 g = 0; g < ng; g++) {
@@ -987,9 +1067,10 @@ extern "C" int hc_decompress_batch(hc_codec *c,
                                    uint64_t *out_off, uint64_t *out_len, int32_t *status)
 {
     if (nf == 0) return 0;
-    HC_CUDA(cudaSetDevice(c->device));
+    HC_ON_DEVICE(c->device);
     const u32 ng = group_count(nf);
     HC_TRY(ensure_kids(c, ng));
+    KidsSync sync_on_exit(c);
     std::vector<GroupJob> jobs(ng);
     // phase 1: upload, FGK decode and the size-only expansion pass of every group
     for (u32 g = 0; g < ng; g++) {

@@ -163,7 +163,8 @@ void hc_host_free(void *p);
  *  out_base              : host buffer of out_cap_total bytes; the files are written back to
  *                          back (each start aligned to 16 bytes); out_off/out_len/status are
  *                          host arrays of nf elements written by the call.
- * status[f]: 0, 6 (-a and len % width != 0), 12 (width/height < 8), HC_E_CAPACITY.
+ * status[f]: 0, 6 (-a and len % width != 0), 12 (width/height < 8), HC_E_CAPACITY (also for a file of 2 GiB or
+ * more: per-file positions inside the transform kernels are 32-bit), HC_E_CODELEN (more than 2^32 - 16 symbols).
  * Returns 0, -(cudaError_t), or HC_E_CAPACITY if out_cap_total is too small. */
 int hc_compress_batch(hc_codec *c,
                       const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,

@@ -18,6 +18,7 @@ enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0 };
 
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }

@@ -106,6 +106,35 @@ def test_decompress_errors(codec, golden, oracle):
     assert bytes(back[-1]) == b"hello world, hello world" and bytes(back[-2]) == bytes(back[-1])
 
 
+def _container(sym, flags, oracle):
+    bits, _ = oracle.fgk_encode(sym)
+    return np.concatenate([np.frombuffer(int(sym.size).to_bytes(8, "little") + bytes([flags]), np.uint8), bits])
+
+
+def test_hostile_adaptive_header_fails_alone(codec, oracle):
+    """A crafted adaptive header (w = h = b = 2^31: 2^62 output bytes promised by 13 payload bytes; the reference dies
+    in its allocation, src/transform.cpp:340) fails with its own status and does not take the batch with it, whatever
+    output capacity the caller offers; a file that merely does not fit reports HC_E_CAPACITY and the size it needs."""
+    cd, _ = codec
+    be = (2 ** 31).to_bytes(8, "big")
+    hostile = _container(np.frombuffer(be * 3 + bytes([0x80]) + bytes(range(13)), np.uint8), 0x40, oracle)
+    huge_b = _container(np.frombuffer((16).to_bytes(8, "big") * 2 + (2 ** 63).to_bytes(8, "big") + bytes([0x80, 7, 7, 7, 200, 1]), np.uint8),
+                        0x40, oracle)
+    good1 = oracle.compress(np.frombuffer(b"hello world, hello world", np.uint8))[1]
+    img = np.arange(64 * 64, dtype=np.uint32).astype(np.uint8)
+    good2 = oracle.compress(img, diff=True, adapt=True, width=64)[1]
+    for cap in (1 << 20, 1 << 26):
+        back, st = cd.decompress([good1, hostile, good2, huge_b], out_cap=cap)
+        assert st[0] == 0 and st[2] == 0 and st[1] in (13, 14) and st[3] in (13, 14), list(st)
+        assert bytes(back[0]) == b"hello world, hello world" and np.array_equal(back[2], img)
+    # too small a buffer: per-file capacity status carrying the need, then one exact retry inside Codec.decompress
+    buf, offs, lens = hc_b200.Codec.pack([good1, good2])
+    rc, out, oo, ol, st = cd.decompress_packed(buf, offs, lens, 64)
+    assert rc == 0 and list(st) == [0, hc_b200.HC_E_CAPACITY] and int(ol[1]) == img.size
+    back, st = cd.decompress([good1, good2], out_cap=64)
+    assert not st.any() and np.array_equal(back[1], img)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", list(MODES))
 def test_samples_golden(golden, samples, mode):
