@@ -641,6 +641,7 @@ struct hc_codec {
     HostBuf htab;
     bool timing = false;
     cudaEvent_t ev[HC_MAX_STAGES + 1];
+    cudaEvent_t wait_ev = nullptr;       // blocking-sync event: host threads waiting for a batch sleep instead of spinning
     const char *stage_names[HC_MAX_STAGES];
     int nstages = 0;
     bool ev_ready = false;
@@ -683,9 +684,19 @@ static void stage_mark(hc_codec *c, const char *name)
     cudaEventRecord(c->ev[c->nstages], c->stream);
 }
 
+// Host-side wait for everything queued on a codec's stream.  With eight processes of four pipeline threads each on one
+// host (bench at N = 8) spinning waits would occupy every core, so the thread sleeps on a blocking-sync event.
+static cudaError_t codec_wait(hc_codec *k)
+{
+    if (!k->wait_ev) return cudaStreamSynchronize(k->stream);
+    cudaError_t e = cudaEventRecord(k->wait_ev, k->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(k->wait_ev);
+}
+
 KidsSync::~KidsSync()
 {
-    for (hc_codec *k : c->kids) cudaStreamSynchronize(k->stream);
+    for (hc_codec *k : c->kids) codec_wait(k);
 }
 
 extern "C" int hc_codec_create(hc_codec **out, int device)
@@ -699,6 +710,7 @@ extern "C" int hc_codec_create(hc_codec **out, int device)
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return -(int)e; }
     for (int i = 0; i <= HC_MAX_STAGES; i++) cudaEventCreate(&c->ev[i]);
+    cudaEventCreateWithFlags(&c->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming);
     c->ev_ready = true;
     *out = c;
     return 0;
@@ -714,6 +726,7 @@ extern "C" void hc_codec_destroy(hc_codec *c)
     c->in.release(); c->a.release(); c->b.release(); c->out.release(); c->tab.release(); c->ws.release(); c->ord.release(); c->jt.release();
     c->htab.release();
     if (c->ev_ready) for (int i = 0; i <= HC_MAX_STAGES; i++) cudaEventDestroy(c->ev[i]);
+    if (c->wait_ev) cudaEventDestroy(c->wait_ev);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1029,7 +1042,7 @@ extern "C" int hc_compress_batch(hc_codec *c,
         const u32 n = j.hi - j.lo;
         const size_t N = n;
         cudaStream_t s = k->stream;
-        HC_CUDA(cudaStreamSynchronize(s));
+        HC_CUDA(codec_wait(k));
         u64 *h = (u64 *)k->htab.p;
         memcpy(out_len + j.lo, h + 7 * N, N * 8);
         memcpy(status + j.lo, h + 8 * N, N * 4);
@@ -1046,8 +1059,7 @@ extern "C" int hc_compress_batch(hc_codec *c,
             total += align_up(len, 16);
         }
         if (total > out_cap_total) {
-            for (u32 q = 0; q < ng; q++) cudaStreamSynchronize(c->kids[q]->stream);
-            return HC_E_CAPACITY;
+            return HC_E_CAPACITY;                          // (KidsSync waits for the groups)
         }
         const u64 gbytes = total - start;
         HC_TRY(k->a.ensure((size_t)gbytes + 512));
@@ -1056,7 +1068,7 @@ extern "C" int hc_compress_batch(hc_codec *c,
         HC_TRY(hc_gather_batch((const u8 *)k->out.p, d + 3 * N, d + 6 * N, (u8 *)k->a.p, d + 5 * N, n, max_out, s));
         if (gbytes) HC_CUDA(cudaMemcpyAsync(out_base + start, k->a.p, (size_t)gbytes, cudaMemcpyDeviceToHost, s));
     }
-    for (u32 g = 0; g < ng; g++) HC_CUDA(cudaStreamSynchronize(c->kids[g]->stream));
+    for (u32 g = 0; g < ng; g++) HC_CUDA(codec_wait(c->kids[g]));
     return 0;
 }
 
@@ -1122,7 +1134,7 @@ extern "C" int hc_decompress_batch(hc_codec *c,
         const u32 n = j.hi - j.lo;
         const size_t N = n;
         cudaStream_t s = k->stream;
-        HC_CUDA(cudaStreamSynchronize(s));
+        HC_CUDA(codec_wait(k));
         u64 *h = (u64 *)k->htab.p;
         memcpy(out_len + j.lo, h + 4 * N, N * 8);
         memcpy(status + j.lo, h + 5 * N, N * 4);
@@ -1151,7 +1163,7 @@ extern "C" int hc_decompress_batch(hc_codec *c,
     }
     for (u32 g = 0; g < ng; g++) {
         hc_codec *k = c->kids[g];
-        HC_CUDA(cudaStreamSynchronize(k->stream));
+        HC_CUDA(codec_wait(k));
         const size_t N = jobs[g].hi - jobs[g].lo;
         const u64 *h = (const u64 *)k->htab.p;
         memcpy(out_len + jobs[g].lo, h + 4 * N, N * 8);

@@ -33,7 +33,10 @@ static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+enum { cudaEventBlockingSync = 1, cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new hc_emu_event(); return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new hc_emu_event(); return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
