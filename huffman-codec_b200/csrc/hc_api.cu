@@ -1186,8 +1186,9 @@ struct hc_pipeline {
     std::vector<Slot> slots;
     std::mutex mu;
     std::condition_variable cv_job, cv_done;
-    std::map<int64_t, int> done;
-    int64_t next_ticket = 0;
+    std::map<int64_t, int> done;         // finished, not yet collected by hc_pipeline_wait
+    int64_t next_ticket = 0, collected_below = 0;
+    std::map<int64_t, bool> collected;   // tickets >= collected_below that were already waited for
     bool stop = false;
 };
 
@@ -1285,9 +1286,12 @@ extern "C" int hc_pipeline_wait(hc_pipeline *p, int64_t ticket)
 {
     std::unique_lock<std::mutex> lk(p->mu);
     if (ticket < 0 || ticket >= p->next_ticket) return -1;
+    if (ticket < p->collected_below || p->collected.count(ticket)) return -1;     // a ticket is waited for once
     p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });
     const int rc = p->done[ticket];
     p->done.erase(ticket);
+    p->collected[ticket] = true;
+    while (p->collected.count(p->collected_below)) p->collected.erase(p->collected_below++);
     return rc;
 }
 

@@ -49,5 +49,6 @@ def test_pipeline_matches_synchronous_calls(name, oracle):
             for f, o, ln in zip(files, r_off, r_len):
                 assert np.array_equal(dec[int(o):int(o) + int(ln)], f)
         assert L.hc_pipeline_wait(pipe, 10 ** 6) != 0            # unknown ticket
+        assert L.hc_pipeline_wait(pipe, djobs[0][0]) != 0        # a ticket is waited for once: no second answer, no hang
     finally:
         L.hc_pipeline_destroy(pipe)
