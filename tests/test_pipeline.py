@@ -106,6 +106,44 @@ def test_decompress_errors(codec, golden, oracle):
     assert bytes(back[-1]) == b"hello world, hello world" and bytes(back[-2]) == bytes(back[-1])
 
 
+def test_mutation_fuzz_matches_oracle(codec, oracle):
+    """Bit flips, truncations and appended bytes in the body of valid .out files (the 9-byte container header and the
+    24 bytes of an adaptive header stay intact, so sizes stay bounded): status and bytes must equal the oracle's for
+    every file of the batch, and a broken file never disturbs its neighbours."""
+    cd, name = codec
+    rng = np.random.default_rng(99)
+    n = 24 if name == "emu" else 48
+    base = []
+    for i in range(6):
+        img = synth.image(synth.CLASSES[i % 4], n, 600 + i, n).reshape(-1)
+        for diff, adapt in ((False, False), (True, True)):
+            base.append(oracle.compress(img, diff=diff, adapt=adapt, width=n)[1])
+    blobs = []
+    for k in range(5 * len(base)):
+        b = base[k % len(base)].copy()
+        kind = k % 5
+        if kind == 0 and b.size > 12:
+            for _ in range(1 + k % 3):
+                b[int(rng.integers(10, b.size))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1 and b.size > 12:
+            b = b[: int(rng.integers(9, b.size))].copy()
+        elif kind == 2:
+            b = np.concatenate([b, rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8)])
+        elif kind == 3 and b.size > 20:
+            i = int(rng.integers(10, b.size - 4))
+            b[i:i + 4] = rng.integers(0, 256, 4, dtype=np.uint8)
+        blobs.append(b)
+    back, st = cd.decompress(blobs)
+    agree = 0
+    for b, got, s in zip(blobs, back, st):
+        rc, exp = oracle.decompress(b)
+        assert int(s) == rc, (int(s), rc)
+        if rc == 0:
+            assert np.array_equal(got, exp)
+            agree += 1
+    assert agree >= len(base)                        # the untouched and the harmlessly extended ones at least
+
+
 def _container(sym, flags, oracle):
     bits, _ = oracle.fgk_encode(sym)
     return np.concatenate([np.frombuffer(int(sym.size).to_bytes(8, "little") + bytes([flags]), np.uint8), bits])
