@@ -387,6 +387,8 @@ constexpr i32 AD_ST_SERIAL = 102;   // internal: block table too small, use the 
 // config 4: one block holds up to a million tokens) go to the CTA-wide kernel, everything else -- blocks of a few
 // dozen tokens, where a step ends at the first block boundary whatever its width -- to the one-warp kernel
 // (measured on the 512 x 512 batch: one warp 6.2 ms, eight cooperating warps 37 ms).
+constexpr u32 AD_WIN_BYTES = 2048;       // token window of the one-warp index kernel (a multiple of 512)
+
 HC_DEV bool ad_index_wide(const AdaptHeader &hd, u64 wide_min) { return hd.b >= 64u && hd.total >= wide_min; }
 
 HC_KERNEL HC_LAUNCH_BOUNDS(32, 1)
@@ -414,6 +416,13 @@ adapt_index_warp_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off,
     u64 pos = 24 + hd.dir_bytes;
     i32 err = 0;
     u64 blk = 0;
+    // The walk advances a few dozen tokens per step (one small block) but looks at 128: the tokens are served from a
+    // 2 KiB shared-memory window that is refilled with coalesced 16-byte loads when the step's range leaves it, so
+    // that a step does not wait for global memory.
+    HC_SHARED HC_ALIGNED16 u8 win[AD_WIN_BYTES];
+    HC_SMEM_ARENA(win);
+    const u32 wina = smem_addr(win);
+    u64 wlo = 0, whi = 0;                          // file positions [wlo, whi) held in the window
     // (crafted headers: block sides beyond 32 bits saturate the block size, offsets that would wrap end the loops)
     for (u64 by = 0; by < hd.h && !err; by = by + hd.b < by ? hd.h : by + hd.b) {
         const u64 bh = hd.h - by < hd.b ? hd.h - by : hd.b;
@@ -426,11 +435,28 @@ adapt_index_warp_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off,
             while (produced < req) {
                 // 128 tokens per step: 4 consecutive bytes per lane
                 const u64 idx = pos + 4u * lane;
+                if (pos < wlo || pos + 128u > whi) {
+                    syncwarp();                            // every lane is done with the old window
+                    wlo = pos & ~(u64)15;
+                    whi = wlo + AD_WIN_BYTES;
+#pragma unroll
+                    for (u32 j = 0; j < AD_WIN_BYTES / 512u; j++) {
+                        const u64 o = wlo + 16u * (lane + 32u * j);
+                        // the 16 bytes that hold the last token lie inside the file's padded region; beyond them: zeros
+                        const uint4 v = o < m ? ldg16(src + o) : make_uint4_zero();
+                        sts32(wina + 16u * (lane + 32u * j), v.x);
+                        sts32(wina + 16u * (lane + 32u * j) + 4u, v.y);
+                        sts32(wina + 16u * (lane + 32u * j) + 8u, v.z);
+                        sts32(wina + 16u * (lane + 32u * j) + 12u, v.w);
+                    }
+                    syncwarp();
+                }
                 u32 b[4], nv = 0;
+                const u32 wo = wina + (u32)(idx - wlo);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const bool v = idx + k < m;
-                    b[k] = v ? src[idx + k] : 0u;
+                    b[k] = v ? lds8(wo + k) : 0u;
                     nv += v ? 1u : 0u;
                 }
                 u32 pb = shfl_up(b[3], 1);
