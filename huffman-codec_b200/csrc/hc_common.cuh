@@ -25,6 +25,7 @@
 #define HC_LAUNCH_BOUNDS(t, b)
 #define HC_RESTRICT
 #define HC_ALIGNED16 __attribute__((aligned(16)))
+#define HC_ALIGNED(n) __attribute__((aligned(n)))
 #else
 #include <cuda_runtime.h>
 #define HC_KERNEL __global__ void
@@ -42,6 +43,7 @@
 #define HC_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #define HC_RESTRICT __restrict__
 #define HC_ALIGNED16 __align__(16)
+#define HC_ALIGNED(n) __align__(n)
 #endif
 
 void hc_count_launch();
@@ -143,6 +145,7 @@ HC_DEV u32 prmt(u32 a, u32 b, u32 sel)
     for (int i = 0; i < 4; i++) r |= (u32)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
     return r;
 }
+HC_DEV u32 prmt_raw(u32 a, u32 b, u32 sel) { return prmt(a, b, sel & 0x7777u); }
 HC_DEV u32 brev(u32 v) { u32 r = 0; for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i); return r; }
 HC_DEV u64 bswap64(u64 v) { return __builtin_bswap64(v); }
 HC_DEV u32 vadd4(u32 a, u32 b)
@@ -167,6 +170,8 @@ HC_DEV u32 funnel_l(u32 lo, u32 hi, u32 sh) { return sh & 31 ? (hi << (sh & 31))
 HC_DEV u32 atomic_add(u32 *p, u32 v) { u32 o = *p; *p = o + v; return o; }
 HC_DEV u64 atomic_add64(u64 *p, u64 v) { u64 o = *p; *p = o + v; return o; }
 HC_DEV void atomic_max_i32(i32 *p, i32 v) { if (v > *p) *p = v; }
+HC_DEV void atomic_min_smem(u32 *p, u32 v) { if (v < *p) *p = v; }
+HC_DEV void atomic_max_smem(u32 *p, u32 v) { if (v > *p) *p = v; }
 // "shared-space addresses": offsets from an arena base (the kernel's __shared__ object)
 inline unsigned char *g_emu_smem_base = nullptr;
 // base = start of the 4 GiB window that holds the kernel's static "shared" objects, so that every
@@ -186,6 +191,7 @@ HC_DEV void sts32_if(bool p, u32 a, u32 v) { if (p) sts32(a, v); }
 HC_DEV void atomic_or_smem(u32 a, u32 v) { sts32(a, lds32(a) | v); }
 HC_DEV uint4 ldg16(const void *p) { uint4 v; memcpy(&v, p, 16); return v; }
 HC_DEV uint4 ldg16_rw(const void *p) { uint4 v; memcpy(&v, p, 16); return v; }
+HC_DEV uint4 ldg16_l1(const void *p) { uint4 v; memcpy(&v, p, 16); return v; }
 HC_DEV void stg16(void *p, uint4 v) { memcpy(p, &v, 16); }
 HC_DEV u32 atomic_or_shared(u32 *p, u32 v) { u32 o = *p; *p = o | v; return o; }
 HC_DEV u8 ldg8(const u8 *p) { return *p; }
@@ -216,6 +222,14 @@ HC_DEV int ffs(u32 v) { return __ffs((int)v); }
 HC_DEV int ffsll(u64 v) { return __ffsll((long long)v); }
 HC_DEV u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
 HC_DEV u32 prmt(u32 a, u32 b, u32 sel) { return __byte_perm(a, b, sel); }
+// PRMT without the selector masking of __byte_perm: only the low 16 bits of sel are read; every selector nibble
+// must be 0..7 (bit 3 would ask for sign replication)
+HC_DEV u32 prmt_raw(u32 a, u32 b, u32 sel)
+{
+    u32 r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 HC_DEV u32 dp4a_u(u32 a, u32 b, u32 c) { return __dp4a(a, b, c); }
 HC_DEV u32 brev(u32 v) { return __brev(v); }
 HC_DEV u64 bswap64(u64 v)
@@ -229,6 +243,8 @@ HC_DEV u32 funnel_l(u32 lo, u32 hi, u32 sh) { return __funnelshift_l(lo, hi, sh)
 HC_DEV u32 atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
 HC_DEV u64 atomic_add64(u64 *p, u64 v) { return atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 HC_DEV void atomic_max_i32(i32 *p, i32 v) { atomicMax(p, v); }
+HC_DEV void atomic_min_smem(u32 *p, u32 v) { atomicMin(p, v); }
+HC_DEV void atomic_max_smem(u32 *p, u32 v) { atomicMax(p, v); }
 // shared-space (32-bit) addressing: tree links are stored as shared addresses so that a walk
 // needs no address arithmetic between dependent loads
 #define HC_SMEM_ARENA(obj) ((void)0)
@@ -259,6 +275,15 @@ HC_DEV uint4 ldg16(const void *p)
 {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// 16-byte load through L1 (read-only path, allocating): for access patterns in which a sector is shared by
+// consecutive loads of the same thread (every thread walks its own contiguous bytes)
+HC_DEV uint4 ldg16_l1(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }

@@ -31,334 +31,350 @@
 
 namespace hcd {
 
-constexpr u32 ENC_STAGE_BYTES = TILE_BYTES + TILE_BYTES / 3 + 64;   // worst case 4/3 + phase
+// ------------------------------------------------------------------------------------------
+// encode
+// ------------------------------------------------------------------------------------------
+// A thread owns ENC_W = 64 CONSECUTIVE input bytes per tile, so that the whole run logic is a handful
+// of 64-bit mask operations per thread and both block scans carry one value per thread.
+constexpr u32 ENC_W = 64;
+constexpr u32 ENC_TILE = TPB * ENC_W;                                    // 16 KiB of input per CTA step
+constexpr u32 ENC_STAGE_BYTES = (ENC_TILE + ENC_TILE / 3 + 64 + 15) & ~15u;  // worst case 4/3 + one carried count + phase
 
-// bit k = (byte k of v == byte k-1), byte -1 = prev (0x100 = none).  Byte-SIMD: one __vcmpeq4 per
-// word against the stream shifted by one byte, then a multiply gathers the 0xFF bytes into bits.
-HC_DEV u32 rle_eq_mask16(const uint4 &v, u32 prev)
-{
-    const u32 K = 0x08040201u;
-    const u32 m0 = vcmpeq4(v.x, (v.x << 8) | (prev & 0xffu));
-    const u32 m1 = vcmpeq4(v.y, funnel_l(v.x, v.y, 8));
-    const u32 m2 = vcmpeq4(v.z, funnel_l(v.y, v.z, 8));
-    const u32 m3 = vcmpeq4(v.w, funnel_l(v.z, v.w, 8));
-    const u32 lo8 = (((m0 & K) | ((m1 & K) << 4)) * 0x01010101u) >> 24;
-    const u32 hi8 = (((m2 & K) | ((m3 & K) << 4)) * 0x01010101u) >> 24;
-    u32 e = lo8 | (hi8 << 8);
-    if (prev > 0xffu) e &= ~1u;
-    return e;
-}
+// Threads write their output bytes at a stride of about 64 bytes = 16 banks, which would serialise the
+// stores of a warp 16-fold; the staging buffer is therefore stored with its 16-byte chunks permuted
+// inside every 128-byte line (chunk ^= line number mod 8): 8 consecutive chunks still fill all 32 banks
+// for the 128-bit copy-out, and chunks 4 apart land in different banks.  `a` = shared address inside a
+// 512-byte aligned buffer.
+HC_DEV u32 stage_swz(u32 a) { return a ^ ((a >> 2) & 0x70u); }
 
-// Output of one 16-element vector.  e: equality bits 0..16 (bit 16 = the element after the vector),
-// valid: bits of existing elements, k0: run index of element 0 if it continues a run (else unused;
-// on return reduced modulo 258).
-//   lit bit k  : element k emits its byte          (run index q = k mod 258 < 3)
-//   cnt bit k  : element k emits the byte q - 2    (last of its run with 2 <= q < 257, or q == 257:
-//                the marker 255 of src/transform.cpp:259-263 is 257 - 2)
-// Pure bit logic.  Runs that start inside the vector cannot reach q = 257; only the
-// leading segment (the elements that continue the incoming run) can, and is patched arithmetically.
-HC_DEV void rle_vec_masks_impl(u32 e, u32 valid, u32 &k0, u32 &lit, u32 &cnt)
-{
-    const bool cont = e & 1u;
-    const bool deep = cont && k0 + 16u >= 257u;
-    if (deep) k0 %= 258u;
-    // bits 1,0 = "e_-1", "e_-2": whether the incoming run already holds >= 2 / >= 3 elements; inside
-    // a long run pretend it does and fix the leading segment below
-    const u32 b1 = (cont && (deep || k0 >= 2u)) ? 2u : 0u, b2 = (cont && (deep || k0 >= 3u)) ? 1u : 0u;
-    const u32 x = ((e & 0xffffu) << 2) | b1 | b2;     // bit k+2 = e_k
-    const u32 q2 = (x >> 2) & (x >> 1);               // e_k & e_k-1           (q >= 2)
-    const u32 q3 = q2 & x;                            // ... & e_k-2           (q >= 3)
-    lit = valid & ~q3;
-    cnt = valid & q2 & ~(e >> 1);                     // run ends here (next element does not continue)
-    if (deep) {
-        const u32 p = (u32)ffs((~e & 0xffffu) | 0x10000u) - 1u;   // elements 0..p-1 continue the incoming run (p >= 1)
-        const u32 lead = (1u << p) - 1u;
-        const u32 kw = 257u - k0;                                 // element with q == 257 (may lie beyond the vector)
-        u32 litl = k0 < 3u ? (1u << (3u - k0)) - 1u : 0u;         // q < 3 at the start ...
-        u32 m255 = 0u;
-        if (kw < 16u) { litl |= 7u << (kw + 1u); m255 = 1u << kw; }   // ... and after the wrap
-        u32 qe = k0 + p - 1u;                                     // run index of the segment's last element
-        if (qe >= 258u) qe -= 258u;
-        const u32 endbit = cnt & (1u << (p - 1u));                // set iff the run ends there
-        lit = (lit & ~lead) | (litl & lead & valid);
-        cnt = (cnt & ~lead) | ((qe >= 2u && qe < 257u) ? endbit : 0u) | (m255 & lead & valid);
-    }
-}
-
-// out-of-line copy (the streaming kernels are instruction-cache bound when everything is inlined four
-// times): lit | cnt << 16 in .x, the reduced k0 in .y
-HC_DEV_NOINLINE uint2 rle_vec_masks(u32 e, u32 valid, u32 k0)
-{
-    u32 lit, cnt;
-    rle_vec_masks_impl(e, valid, k0, lit, cnt);
-    uint2 r; r.x = lit | (cnt << 16); r.y = k0;
-    return r;
-}
-
-// run index modulo 258 of element k of a vector (k0: as returned by rle_vec_masks)
-HC_DEV u32 rle_run_index(u32 e, u32 k0, u32 k)
-{
-    const u32 zeros = ~e & ((2u << k) - 1u);          // run starts at or below k
-    if (zeros) return k - (31u - (u32)clz(zeros));
-    const u32 q = k0 + k;
-    return q >= 258u ? q - 258u : q;
-}
-
-// byte-granular writer into the shared staging buffer: bytes are assembled in a register pair,
-// full words go out as STS.32, the ragged first/last bytes as STS.U8 (neighbouring threads own the
-// other bytes of those words)
-struct StageWriter {
-    u32 lo, hi;    // lo: the word being assembled (fill < 4 valid bytes between calls)
-    u32 fill;      // bytes in lo (including the leading filler of the first word)
-    u32 waddr;     // shared address of the word being assembled
-    u32 skip;      // filler bytes of the first word still to be skipped (0 after the first flush)
+struct RleEncShared {
+    u8 stage[ENC_STAGE_BYTES];   // first member: 512-byte aligned like the object
+    u32 lut[256];
+    u32 wtot[2][NW];
+    u32 carry;
 };
 
-HC_DEV void sw_init(StageWriter &w, u32 stage_addr, u32 o)
+HC_DEV RleEncShared *rle_enc_shared()
 {
-    w.lo = 0; w.hi = 0;
-    w.fill = o & 3u;
-    w.skip = o & 3u;
-    w.waddr = stage_addr + (o & ~3u);
+    HC_SHARED HC_ALIGNED(512) RleEncShared sh;
+    return &sh;
 }
 
-HC_DEV void sw_flush_word(StageWriter &w)
-{
-    if (w.skip) {                                      // bytes skip..3 (skip = 1..3), predicated stores
-        if (w.skip <= 1u) sts8(w.waddr + 1u, w.lo >> 8);
-        if (w.skip <= 2u) sts8(w.waddr + 2u, w.lo >> 16);
-        sts8(w.waddr + 3u, w.lo >> 24);
-        w.skip = 0;
-    } else {
-        sts32(w.waddr, w.lo);
-    }
-    w.waddr += 4u;
-    w.lo = w.hi;
-    w.hi = 0;
-    w.fill -= 4u;
-}
-
-// append the low nb (0..4) bytes of x; the bytes of x above nb must be zero
-HC_DEV void sw_put(StageWriter &w, u32 x, u32 nb)
-{
-    const u32 s = 8u * w.fill;
-    w.lo |= x << s;
-    w.hi = funnel_l(x, 0u, s);          // bytes that spill into the next word (0 when s == 0)
-    w.fill += nb;
-    if (w.fill >= 4u) sw_flush_word(w);
-}
-
-HC_DEV void sw_put_byte(StageWriter &w, u32 b) { sw_put(w, b & 0xffu, 1u); }
-HC_DEV void sw_put_word(StageWriter &w, u32 x) { sw_put(w, x, 4u); }
-
-HC_DEV void sw_finish(StageWriter &w)
-{
-    // bytes skip..fill-1 of the last word (fill <= 3)
-    if (w.skip == 0u && w.fill > 0u) sts8(w.waddr, w.lo);
-    if (w.skip <= 1u && w.fill > 1u) sts8(w.waddr + 1u, w.lo >> 8);
-    if (w.skip <= 2u && w.fill > 2u) sts8(w.waddr + 2u, w.lo >> 16);
-}
-
-// 16 bytes to the byte offset o of a shared staging buffer whose neighbouring bytes belong to other
-// threads: whole words where possible, byte stores for the two ragged words
-HC_DEV void stage_put16(u32 stage_addr, u32 o, const uint4 &v)
-{
-    const u32 r = o & 3u, a = stage_addr + (o & ~3u);
-    if (r == 0u) {
-        sts32(a, v.x); sts32(a + 4u, v.y); sts32(a + 8u, v.z); sts32(a + 12u, v.w);
-    } else {
-        const u32 s = 8u * r;
-        const u32 w0 = v.x << s, w4 = v.w >> (32u - s);
-        if (r <= 1u) sts8(a + 1u, w0 >> 8);
-        if (r <= 2u) sts8(a + 2u, w0 >> 16);
-        sts8(a + 3u, w0 >> 24);
-        sts32(a + 4u, funnel_l(v.x, v.y, s));
-        sts32(a + 8u, funnel_l(v.y, v.z, s));
-        sts32(a + 12u, funnel_l(v.z, v.w, s));
-        sts8(a + 16u, w4);
-        if (r >= 2u) sts8(a + 17u, w4 >> 8);
-        if (r >= 3u) sts8(a + 18u, w4 >> 16);
-    }
-}
-
-// Compaction table of the encoder.  Index = m4 | b4 << 4 for one 4-element word: m4 = elements that
-// emit their byte (a literal, or a count already substituted into the word), b4 (subset of m4) =
-// elements followed by a count byte 0 (a run of exactly three ends there).  Entry = two PRMT
-// selectors (low / high output word) that move the kept bytes together and insert the zero bytes
-// (selector nibble 4 = byte 0 of the second PRMT operand, which is zero).
-HC_DEV u32 *rle_enc_lut()
-{
-    HC_SHARED u32 lut[256];
-    return lut;
-}
-
+// Compaction table of the encoder.  Index = k4 | p4 << 4 for the four elements of one input word:
+// k4 = elements that emit their own byte, p4 (subset of k4) = elements whose byte is preceded by the
+// count byte of the run that ended just before them.  Entry = two PRMT selectors (low / high output
+// word) that move the kept bytes together and leave a zero byte where a count goes (selector nibble
+// 4 = byte 0 of the second PRMT operand, which is zero).
 // called once per kernel by all TPB threads before the first rle_encode_stream
 HC_DEV void rle_enc_init()
 {
-    u32 *lut = rle_enc_lut();
-    const u32 idx = threadIdx.x & 255u, m4 = idx & 15u, b4 = idx >> 4;
+    RleEncShared *sh = rle_enc_shared();
+    const u32 idx = threadIdx.x & 255u, k4 = idx & 15u, p4 = idx >> 4;
     u64 sel = 0x4444444444444444ull;
     u32 o = 0;
     for (u32 k = 0; k < 4u; k++) {
-        if ((m4 >> k) & 1u) {
+        if ((k4 >> k) & 1u) {
+            if ((p4 >> k) & 1u) o++;                      // nibble stays 4: the count byte's place
             sel = (sel & ~(0xfull << (4u * o))) | ((u64)k << (4u * o));
             o++;
-            if ((b4 >> k) & 1u) o++;                  // nibble stays 4: a zero byte
         }
     }
-    lut[idx] = (u32)(sel & 0xffffu) | ((u32)((sel >> 16) & 0xffffu) << 16);
+    sh->lut[idx] = (u32)(sel & 0xffffu) | ((u32)((sel >> 16) & 0xffffu) << 16);
     syncthreads();
 }
 
-// writes the output bytes of one vector (masks from rle_vec_masks) to the staging buffer at byte o
-HC_DEV_NOINLINE void rle_stage_vector(uint4 v, u32 lit, u32 cbm, u32 eq, u32 k0, u32 stage, u32 o, const u32 *lut)
+// 0x80 in every byte of the result where the byte of d is zero (exact, no borrow between bytes)
+HC_DEV u32 rle_zero_bytes(u32 d)
 {
-    if (lit == 0xffffu && cbm == 0u) {                    // all literals: the vector goes out verbatim
-        stage_put16(stage, o, v);
-        return;
-    }
-    StageWriter w;
-    sw_init(w, stage, o);
-    {
-        // word by word: substitute the count of a run that ends on a non-literal element into its
-        // byte (at most one per word: such elements are >= 4 apart), then compact
-        const u32 keep = lit | cbm, both = lit & cbm, sub = cbm & ~lit;
+    const u32 t = (d & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | d) & 0x80808080u;
+}
+
+// 128 * (eight equality bits) of the words a, b (a first): bit k = byte k equals the byte before it;
+// pw = the word before a
+HC_DEV u32 rle_eq8x128(u32 pw, u32 a, u32 b)
+{
+    const u32 za = rle_zero_bytes(a ^ funnel_l(pw, a, 8)), zb = rle_zero_bytes(b ^ funnel_l(a, b, 8));
+    return dp4a_u(za, 0x08040201u, dp4a_u(zb, 0x80402010u, 0u));
+}
+
+// equality bits of 32 consecutive bytes v0, v1; pw = the word before them
+HC_DEV u32 rle_eq32(u32 pw, const uint4 &v0, const uint4 &v1)
+{
+    const u32 m0 = rle_eq8x128(pw, v0.x, v0.y), m1 = rle_eq8x128(v0.y, v0.z, v0.w);
+    const u32 m2 = rle_eq8x128(v0.w, v1.x, v1.y), m3 = rle_eq8x128(v1.y, v1.z, v1.w);
+    return (m0 >> 7) | (m1 << 1) | (m2 << 9) | (m3 << 17);
+}
+
+// exclusive block scan of one value per thread; wtot: NW words that no other scan touches before the
+// next barrier after this call.  Returns the fold of the whole block.
+template <class Op>
+HC_DEV u32 block_scan1(u32 v, u32 &excl, u32 identity, Op op, u32 *wtot)
+{
+    static_assert(NW == 8, "the cross-warp step scans eight partials");
+    const u32 lane = lane_id(), w = warp_id();
+    u32 inc = v;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            u32 x = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
-            const u32 s4 = (sub >> (4 * i)) & 15u;
-            if (s4) {
-                const u32 kk = (u32)ffs(s4) - 1u;
-                const u32 val = rle_run_index(eq, k0, 4u * i + kk) - 2u;
-                x = (x & ~(0xffu << (8u * kk))) | (val << (8u * kk));
-            }
-            const u32 idx = ((keep >> (4 * i)) & 15u) | (((both >> (4 * i)) & 15u) << 4);
-            const u32 nb = (u32)popc(idx);
-            if (nb == 0u) continue;
-            const u32 e = lut[idx];
-            sw_put(w, prmt(x, 0u, e & 0xffffu), nb < 4u ? nb : 4u);
-            if (nb > 4u) sw_put(w, prmt(x, 0u, e >> 16), nb - 4u);
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 t = shfl_up(inc, d);
+        if (lane >= (u32)d) inc = op(t, inc);
     }
-    sw_finish(w);
+    if (lane == 31) wtot[w] = inc;
+    syncthreads();
+    u32 pin = wtot[lane & 7u];                            // every group of eight lanes scans the eight partials
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const u32 t = shfl_up(pin, d);
+        if ((lane & 7u) >= (u32)d) pin = op(t, pin);
+    }
+    const u32 total = shfl(pin, 7);
+    u32 base = shfl(pin, (int)(w ? w - 1u : 0u));
+    if (w == 0) base = identity;
+    u32 le = shfl_up(inc, 1);
+    if (lane == 0) le = identity;
+    excl = op(base, le);
+    return total;
+}
+
+// Branch-free byte appender into the (permuted) staging buffer.  Bytes collect in w0; a word goes out with one
+// STS.32 as soon as it is complete.  A thread's first word may hold bytes of the thread before it: that word is
+// kept back (`head`) and its bytes are stored one by one at the end, like the incomplete last word.
+struct EncWriter {
+    u32 w0;        // the word being assembled (fill < 4 valid bytes between calls, including leading filler)
+    u32 fill;
+    u32 waddr;     // logical shared address of the word being assembled
+    u32 first;     // address of the first word if it starts with filler (shared with the thread before), else ~0
+    u32 skip;      // filler bytes of the first word
+    u32 head;      // the completed first word, if it is a shared one
+};
+
+HC_DEV void ew_init(EncWriter &w, u32 stage_addr, u32 o)
+{
+    w.w0 = 0; w.head = 0;
+    w.fill = o & 3u;
+    w.skip = o & 3u;
+    w.waddr = stage_addr + (o & ~3u);
+    w.first = w.skip ? w.waddr : 0xffffffffu;
+}
+
+// append the low nb (0..8) bytes of hi:lo; the bytes above nb must be zero
+HC_DEV void ew_put8(EncWriter &w, u32 lo, u32 hi, u32 nb)
+{
+    const u32 s = 8u * w.fill;
+    const u32 a0 = w.w0 | (lo << s), a1 = funnel_l(lo, hi, s), a2 = funnel_l(hi, 0u, s);
+    const u32 f = w.fill + nb;                      // 0..11
+    const bool shared = w.waddr == w.first;
+    if (f >= 4u && !shared) sts32(stage_swz(w.waddr), a0);
+    if (f >= 4u && shared) w.head = a0;
+    if (f >= 8u) sts32(stage_swz(w.waddr + 4u), a1);
+    w.w0 = f >= 8u ? a2 : (f >= 4u ? a1 : a0);
+    w.waddr += f & ~3u;
+    w.fill = f & 3u;
+}
+
+// append the low nb (0..4) bytes of x
+HC_DEV void ew_put4(EncWriter &w, u32 x, u32 nb)
+{
+    const u32 s = 8u * w.fill;
+    const u32 a0 = w.w0 | (x << s), a1 = funnel_l(x, 0u, s);
+    const u32 f = w.fill + nb;                      // 0..7
+    const bool shared = w.waddr == w.first;
+    if (f >= 4u && !shared) sts32(stage_swz(w.waddr), a0);
+    if (f >= 4u && shared) w.head = a0;
+    w.w0 = f >= 4u ? a1 : a0;
+    w.waddr += f & ~3u;
+    w.fill = f & 3u;
+}
+
+// append 16 bytes
+HC_DEV void ew_put16(EncWriter &w, const uint4 &v)
+{
+    const u32 s = 8u * w.fill;
+    const u32 a0 = w.w0 | (v.x << s);
+    if (w.waddr == w.first) w.head = a0;
+    else sts32(stage_swz(w.waddr), a0);
+    sts32(stage_swz(w.waddr + 4u), funnel_l(v.x, v.y, s));
+    sts32(stage_swz(w.waddr + 8u), funnel_l(v.y, v.z, s));
+    sts32(stage_swz(w.waddr + 12u), funnel_l(v.z, v.w, s));
+    w.waddr += 16u;
+    w.w0 = funnel_l(v.w, 0u, s);
+}
+
+HC_DEV void ew_finish(EncWriter &w)
+{
+    if (w.skip && w.waddr != w.first) {
+        // bytes skip..3 of the first word (skip = 1..3)
+        const u32 a = stage_swz(w.first);
+        if (w.skip <= 1u) sts8(a + 1u, w.head >> 8);
+        if (w.skip <= 2u) sts8(a + 2u, w.head >> 16);
+        sts8(a + 3u, w.head >> 24);
+        w.skip = 0;
+    }
+    // bytes skip..fill-1 of the last word (fill <= 3); skip != 0 only if the first word is the last one too
+    const u32 a = stage_swz(w.waddr);
+    if (w.skip == 0u && w.fill > 0u) sts8(a, w.w0);
+    if (w.skip <= 1u && w.fill > 1u) sts8(a + 1u, w.w0 >> 8);
+    if (w.skip <= 2u && w.fill > 2u) sts8(a + 2u, w.w0 >> 16);
 }
 
 // Encodes the n-byte stream at src (16-byte aligned) to dst (any alignment); called by all TPB
 // threads of a CTA, returns the number of bytes written.  Ends with a CTA barrier.  The kernel must
 // have called rle_enc_init() before.
+//
+// Causal form of src/transform.cpp:241-279: with q = index of an element inside its maximal run
+// modulo 258 (runs are taken over elements 0..n-2, the last element is a run of its own), element k emits
+//      [the count q' - 2 of the run that ended at k-1, if k starts a run and 2 <= q' < 257]
+//      [its byte, if q < 3]   or   [255, if q == 257]
+// so that everything a thread emits follows from its own bytes, the byte before them and the length of
+// the run that reaches into them (a block-wide max-scan of run-start positions).
 HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT dst)
 {
-    HC_SHARED u32 wtot[2][32];
-    HC_SHARED u32 s_carry_run;
-    HC_SHARED HC_ALIGNED16 u8 sout[ENC_STAGE_BYTES];
-    HC_SMEM_ARENA(wtot);
+    RleEncShared *sh = rle_enc_shared();
+    HC_SMEM_ARENA(*sh);
     const u32 tid = threadIdx.x, lane = tid & 31;
-    const u32 stage = smem_addr(sout);
+    const u32 stage = smem_addr(sh->stage);
     const u32 dphase = (u32)((uintptr_t)dst & 15u);
-    const u32 *lut = rle_enc_lut();
-    {
-        u64 out_pos = 0;      // bytes emitted by all previous tiles
-        u32 carry_run = 0;    // length of the run that ends at the last element of the previous tile
+    const u32 base = tid * ENC_W;
+    const u32 *lut = sh->lut;
+    u64 out_pos = 0;      // bytes emitted by all previous tiles
+    u32 carry = 0;        // length modulo 258 of the run that ends at the last element of the previous tile
 
-        // halo: lane 0 needs the byte before its vector, lane 31 the byte after (other lanes get them
-        // by shuffle); fetched one tile ahead like the vectors themselves
-        uint4 cur[UN], nxt[UN];
-        u32 hcur[UN], hnxt[UN];
+    // one tile ahead: the 64 bytes of the thread and, for lane 0, the byte before them (the other lanes
+    // get it by shuffle)
+    uint4 nx[4];
+    u32 hn = 0;
 #pragma unroll
-        for (int j = 0; j < UN; j++) {
-            u64 p = (u64)j * SUB_BYTES + tid * 16;
-            cur[j] = p < n ? ldg16(src + p) : make_uint4_zero();
-            hcur[j] = 0x100u;
-            if (lane == 0 && p > 0 && p < n) hcur[j] = ldg8(src + p - 1);
-            if (lane == 31 && p + 16 < n) hcur[j] = ldg8(src + p + 16);
-        }
-        for (u64 t0 = 0; t0 < n; t0 += TILE_BYTES) {
-#pragma unroll
-            for (int j = 0; j < UN; j++) {
-                u64 p = t0 + TILE_BYTES + (u64)j * SUB_BYTES + tid * 16;
-                nxt[j] = p < n ? ldg16(src + p) : make_uint4_zero();
-                hnxt[j] = 0x100u;
-                if (lane == 0 && p < n) hnxt[j] = ldg8(src + p - 1);
-                if (lane == 31 && p + 16 < n) hnxt[j] = ldg8(src + p + 16);
-            }
-            // ---- equality bits and run starts ------------------------------------------
-            u32 eq[UN];      // bit k (0..16): element k equals element k-1 (bit 16 = next thread's first)
-            u32 valid[UN];   // bit k: element exists
-            u32 smax[UN], sexcl[UN];
-#pragma unroll
-            for (int j = 0; j < UN; j++) {
-                const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
-                const u32 first = cur[j].x & 0xffu, last = cur[j].w >> 24;
-                u32 pb = shfl_up(last, 1), nb = shfl_down(first, 1);
-                if (lane == 0) pb = hcur[j];
-                if (lane == 31) nb = hcur[j];
-                u32 e = rle_eq_mask16(cur[j], pb);
-                if (nb == last) e |= 1u << 16;
-                const u32 vm = p >= n ? 0u : (n - p >= 17 ? 0x1ffffu : ((1u << (u32)(n - p)) - 1u));
-                // the last element of the file never continues a run (forced literal)
-                if (n - 1 >= p && n - 1 - p <= 16) e &= ~(1u << (u32)(n - 1 - p));
-                e &= vm;
-                eq[j] = e;
-                valid[j] = vm & 0xffffu;
-                const u32 starts = valid[j] & ~e;
-                // tile-relative position + 1 of the last run start owned by this thread
-                smax[j] = starts ? (u32)j * SUB_BYTES + tid * 16 + (31u - (u32)clz(starts)) + 1u : 0u;
-            }
-            block_scan_striped(smax, sexcl, 0u, OpMax(), wtot[0]);
-
-            // ---- per-vector output masks and counts ----------------------------------------
-            u32 cnt[UN], oexcl[UN], k0v[UN], lit[UN], cbm[UN];
-#pragma unroll
-            for (int j = 0; j < UN; j++) {
-                const u32 tp = (u32)j * SUB_BYTES + tid * 16;   // tile-relative position
-                u32 k0 = sexcl[j] ? tp - (sexcl[j] - 1u) : carry_run + tp;   // run index of element 0
-                if (j == UN - 1 && tid == TPB - 1) {
-                    // length of the run that ends at the last element of a full tile (kept below
-                    // 2^15 + 258: only its value modulo 258 and "is it long" matter)
-                    const u32 st = valid[j] & ~eq[j];
-                    u32 cr = st ? 16u - (31u - (u32)clz(st)) : ((eq[j] & 1u) ? k0 + 16u : 16u);
-                    if (cr >= 258u * 128u) cr = 258u * 64u + cr % 258u;
-                    s_carry_run = cr;
-                }
-                const uint2 mk = rle_vec_masks(eq[j], valid[j], k0);
-                lit[j] = mk.x & 0xffffu;
-                cbm[j] = mk.x >> 16;
-                k0v[j] = mk.y;
-                cnt[j] = (u32)popc(mk.x);
-            }
-            u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
-
-            // ---- stage the output bytes -------------------------------------------------
-            const u32 shift = (u32)((dphase + out_pos) & 15u);
-#pragma unroll
-            for (int j = 0; j < UN; j++) {
-                if (cnt[j] == 0) continue;
-                rle_stage_vector(cur[j], lit[j], cbm[j], eq[j], k0v[j], stage, shift + oexcl[j], lut);
-            }
-            syncthreads();
-            carry_run = s_carry_run;
-            // ---- copy out: sout[shift .. shift+total) -> dst[out_pos ..) ---------------------
-            {
-                u8 *gbase = dst + out_pos - shift;              // 16-byte aligned
-                const u32 end = shift + total;
-                const u32 nchunk = (end + 15u) / 16u;
-                for (u32 c = tid; c < nchunk; c += TPB) {
-                    u32 lo = c * 16u, hi = lo + 16u;
-                    if (lo >= shift && hi <= end) {
-                        stg16(gbase + lo, *(const uint4 *)(sout + lo));
-                    } else {
-                        u32 a = lo < shift ? shift : lo, b = hi > end ? end : hi;
-                        for (u32 i = a; i < b; i++) gbase[i] = sout[i];
-                    }
-                }
-            }
-            out_pos += total;
-#pragma unroll
-            for (int j = 0; j < UN; j++) { cur[j] = nxt[j]; hcur[j] = hnxt[j]; }
-            syncthreads();
-        }
-        return out_pos;
+    for (int i = 0; i < 4; i++) {
+        const u64 p = (u64)base + 16u * i;
+        nx[i] = p < n ? ldg16_l1(src + p) : make_uint4_zero();
     }
+    if (lane == 0 && base > 0 && base < n) hn = ldg8(src + base - 1);
+    for (u64 t0 = 0; t0 < n; t0 += ENC_TILE) {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = nx[i];
+        const u32 hb = hn;
+        const u64 g0 = t0 + base;                     // file position of this thread's element 0
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u64 p = g0 + ENC_TILE + 16u * i;
+            nx[i] = p < n ? ldg16_l1(src + p) : make_uint4_zero();
+        }
+        if (lane == 0 && g0 + ENC_TILE < n) hn = ldg8(src + g0 + ENC_TILE - 1);
+
+        // ---- equality bits, run starts -----------------------------------------------------
+        u32 pb = shfl_up(v[3].w >> 24, 1);
+        if (lane == 0) pb = hb;
+        u64 E = (u64)rle_eq32(pb << 24, v[0], v[1]) | ((u64)rle_eq32(v[1].w, v[2], v[3]) << 32);
+        u64 V = ~0ull;
+        if (g0 == 0) E &= ~1ull;                      // nothing before the first element
+        if (g0 + ENC_W >= n) {
+            // ragged end: the file's last element lies in this segment, or the segment (partly) beyond it
+            const u32 cv = g0 < n ? (u32)(n - g0) : 0u;
+            V = cv >= 64u ? ~0ull : ((1ull << cv) - 1ull);
+            if (cv) E &= ~(1ull << (cv - 1u));        // the last element never continues a run
+            E &= V;
+        }
+        const u64 S = V & ~E;                         // run starts
+        // tile-relative position + 1 of the last run start owned by this thread
+        const u32 smax = S ? base + (63u - (u32)clzll(S)) + 1u : 0u;
+        u32 sexcl;
+        block_scan1(smax, sexcl, 0u, OpMax(), sh->wtot[0]);
+
+        // ---- what every element emits ---------------------------------------------------------
+        // r_in = length of the run that ends at the element before this segment, z = r_in mod 258 = run
+        // index of element 0 if it continues that run
+        const u32 r_in = sexcl ? base - (sexcl - 1u) : carry + base;
+        const u32 z = r_in % 258u;
+        const bool cont = (u32)E & 1u;
+        u64 Eq = E;                                   // E with the places cleared where q restarts at 0
+        if (cont && z == 0u) Eq &= ~1ull;
+        u64 wrap = 0;                                 // the element with q == 257 (emits 255)
+        if (cont && z >= 258u - ENC_W) {
+            const u32 kw = 257u - z;                  // < 64; only if the run gets that far
+            if ((~E & ((2ull << kw) - 1ull)) == 0ull) {
+                wrap = 1ull << kw;
+                Eq &= ~(2ull << kw);
+            }
+        }
+        const u32 c1 = z >= 2u ? 1u : 0u, c2 = z >= 3u ? 1u : 0u;   // "e" bits of the elements -1, -2
+        const u64 e1 = (Eq << 1) | c1, e2 = (Eq << 2) | (c1 << 1) | c2;
+        const u64 q3 = Eq & e1 & e2;                  // q >= 3
+        const u64 keep = (V & ~q3) | wrap;            // emits its byte (255 for the wrap element, patched below)
+        const u64 pre = S & e1 & e2 & ~(wrap << 1);   // starts a run and the run before it has 2 <= q' < 257
+        const u64 Sq = V & ~Eq;                       // places where q == 0
+        const u32 cnt = (u32)popcll(keep) + (u32)popcll(pre);
+        if (tid == TPB - 1) {
+            // run length modulo 258 at the last element of a full tile
+            sh->carry = Sq ? (u32)clzll(Sq) + 1u : (z + ENC_W) % 258u;
+        }
+        u32 oexcl;
+        const u32 total = block_scan1(cnt, oexcl, 0u, OpAdd(), sh->wtot[1]);
+
+        // ---- stage the output bytes -------------------------------------------------
+        const u32 shift = (u32)((dphase + out_pos) & 15u);
+        if (cnt) {
+            const u32 o = shift + oexcl;
+            EncWriter w;
+            ew_init(w, stage, o);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const u32 k16 = (u32)(keep >> (16 * g)) & 0xffffu, p16 = (u32)(pre >> (16 * g)) & 0xffffu;
+                if (k16 == 0u) continue;
+                if (k16 == 0xffffu && p16 == 0u) { ew_put16(w, v[g]); continue; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const u32 idx = ((k16 >> (4 * j)) & 15u) | (((p16 >> (4 * j)) & 15u) << 4);
+                    const u32 x = vec_word(v[g], j), e = lut[idx];
+                    ew_put8(w, prmt_raw(x, 0u, e), prmt_raw(x, 0u, e >> 16), (u32)popc(idx));
+                }
+            }
+            ew_finish(w);
+            // count bytes (into the places the table left open) and the 255 of a wrap, 32 elements at a time
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const u32 keep_h = (u32)(keep >> (32 * h)), pre_h = (u32)(pre >> (32 * h));
+                const u32 sq_h = (u32)(Sq >> (32 * h)), wrap_h = (u32)(wrap >> (32 * h));
+                const u32 obase = h ? o + (u32)popc((u32)keep) + (u32)popc((u32)pre) : o;
+                // q of the element before this half
+                const u32 qb = h == 0 ? z - 1u : ((u32)Sq ? (u32)clz((u32)Sq) : z + 31u);
+                u32 todo = pre_h | wrap_h;
+                while (todo) {
+                    const u32 k = (u32)ffs(todo) - 1u;
+                    todo &= todo - 1u;
+                    const u32 below = (1u << k) - 1u;
+                    const u32 pos = obase + (u32)popc(keep_h & below) + (u32)popc(pre_h & below);
+                    const u32 sb = sq_h & below;
+                    // q of element k-1, minus 2 (255 for the wrap element)
+                    u32 val = (sb ? k - 1u - (31u - (u32)clz(sb)) : qb + k) - 2u;
+                    if ((wrap_h >> k) & 1u) val = 255u;
+                    sts8(stage_swz(stage + pos), val);
+                }
+            }
+        }
+        syncthreads();
+        carry = sh->carry;
+        // ---- copy out: stage[shift .. shift+total) -> dst[out_pos ..) ---------------------
+        {
+            u8 *gbase = dst + out_pos - shift;              // 16-byte aligned
+            const u32 end = shift + total;
+            const u32 nchunk = (end + 15u) / 16u;
+            for (u32 c = tid; c < nchunk; c += TPB) {
+                const u32 lo = c * 16u, hi = lo + 16u;
+                if (lo >= shift && hi <= end) {
+                    const uint2 a = lds64(stage_swz(stage + lo)), b = lds64(stage_swz(stage + lo) + 8u);
+                    uint4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+                    stg16(gbase + lo, r);
+                } else {
+                    const u32 a = lo < shift ? shift : lo, b = hi > end ? end : hi;
+                    for (u32 i = a; i < b; i++) gbase[i] = (u8)lds8(stage_swz(stage + i));
+                }
+            }
+        }
+        out_pos += total;
+        syncthreads();
+    }
+    return out_pos;
 }
 
 HC_KERNEL HC_LAUNCH_BOUNDS(256, 3)
@@ -382,39 +398,58 @@ constexpr u32 MAP_NE = 0x00010101u;   // byte differs from previous: 0->1 1->1 2
 constexpr u32 MAP_EQ = 0x00030201u;   // byte equals previous:       0->1 1->2 2->3 3->0
 
 HC_DEV u32 map_apply(u32 m, u32 s) { return (m >> (8u * s)) & 3u; }
-// first a then b
-HC_DEV u32 map_compose(u32 a, u32 b)
+// a map as a PRMT selector (one nibble per state)
+HC_DEV u32 map_sel(u32 a)
 {
-    const u32 y = (a | (a >> 4)) & 0x00ff00ffu;       // bytes -> nibbles: the PRMT selector
-    return prmt(b, 0u, (y | (y >> 8)) & 0xffffu);
+    const u32 y = (a | (a >> 4)) & 0x00ff00ffu;
+    return (y | (y >> 8)) & 0xffffu;
 }
+// first a then b
+HC_DEV u32 map_compose(u32 a, u32 b) { return prmt_raw(b, 0u, map_sel(a)); }
 struct OpCompose { HC_DEVM u32 operator()(u32 a, u32 b) const { return map_compose(a, b); } };
 
-constexpr u32 DEC_WIN = TPB * 64;   // 16 KiB of output per expansion window
+constexpr u32 DEC_W = 64;                      // token bytes per thread per tile
+constexpr u32 DEC_TILE = TPB * DEC_W;          // 16 KiB of tokens per CTA step
+constexpr u32 DEC_WIN = 16384;                 // output bytes per expansion window
+constexpr u32 DEC_MAXRUN = DEC_TILE / 4 + 8;   // a count byte needs three literals before it
+constexpr u32 DEC_MAXOUT = 16u * 255u + 48u;   // most output bytes of one thread's 64 tokens
+constexpr u32 DEC_STAGE = DEC_WIN + ((DEC_MAXOUT + 15u) & ~15u) + 80u;
 
 // Tables of the decoder, indexed by 8 consecutive equality bits (bit k: byte k equals byte k-1):
-//   map8[e8]        the state map of those 8 bytes
+//   map8[e8]        the state map of those 8 bytes, sel8[e8] the same map as a PRMT selector
 //   cls8[s][e8]     entering in state s: bits 0..7 = which of the 8 bytes are COUNT bytes (read in
 //                   state 3), bits 8..9 = the state after them
-struct RleDecTables {
+//   lut4[m4]        PRMT selector that moves the bytes m4 of a word together
+struct RleDecShared {
+    u8 stage[DEC_STAGE];         // first member: 512-byte aligned like the object; permuted as the encoder's
+    u32 rpos[DEC_MAXRUN];        // runs of the tile: position (shifted tile coordinates) | length << 22
+    u8 rval[DEC_MAXRUN];         // ... and their byte
     u32 map8[256];
+    u16 sel8[256];
     u16 cls8[4][256];
+    u32 lut4[16];
+    u32 wtot[2][NW];
+    u64 wtot64[NW];
+    u32 ilo, ihi;                // runs of the threads of the current window
+    u32 wend;                    // end of their output
 };
+static_assert(sizeof(RleDecShared) <= 47u * 1024u, "static shared memory");
 
-HC_DEV RleDecTables *rle_dec_tables()
+HC_DEV RleDecShared *rle_dec_shared()
 {
-    HC_SHARED RleDecTables t;
-    return &t;
+    HC_SHARED HC_ALIGNED(512) RleDecShared sh;
+    return &sh;
 }
 
 // called once per kernel by all TPB threads before the first rle_decode_stream
 HC_DEV void rle_dec_init()
 {
-    RleDecTables *t = rle_dec_tables();
+    RleDecShared *t = rle_dec_shared();
     const u32 e8 = threadIdx.x & 255u;
     u32 m = MAP_ID;
     for (u32 k = 0; k < 8u; k++) m = map_compose(m, ((e8 >> k) & 1u) ? MAP_EQ : MAP_NE);
     t->map8[e8] = m;
+    t->sel8[e8] = (u16)map_sel(m);
     for (u32 s0 = 0; s0 < 4u; s0++) {
         u32 st = s0, cm = 0;
         for (u32 k = 0; k < 8u; k++) {
@@ -423,26 +458,32 @@ HC_DEV void rle_dec_init()
         }
         t->cls8[s0][e8] = (u16)(cm | (st << 8));
     }
+    if (e8 < 16u) {
+        u32 sel = 0x4444u, o = 0;
+        for (u32 k = 0; k < 4u; k++)
+            if ((e8 >> k) & 1u) { sel = (sel & ~(0xfu << (4u * o))) | (k << (4u * o)); o++; }
+        t->lut4[e8] = sel;
+    }
     syncthreads();
 }
 
-// state map of the valid bytes of a ragged vector (first / last vector of a stream)
-HC_DEV_NOINLINE u32 rle_dec_map_partial(u32 e, u32 vm)
+// state map of the valid bytes vm of a ragged 64-byte segment (first / last segment of a stream)
+HC_DEV_NOINLINE u32 rle_dec_map_partial(u64 e, u64 vm)
 {
     u32 m = MAP_ID;
-    for (u32 k = 0; k < 16u; k++)
-        if ((vm >> k) & 1u) m = map_compose(m, ((e >> k) & 1u) ? MAP_EQ : MAP_NE);
+    for (u32 k = 0; k < 64u; k++)
+        if ((vm >> k) & 1ull) m = map_compose(m, ((e >> k) & 1ull) ? MAP_EQ : MAP_NE);
     return m;
 }
 
-// count-byte mask of the valid bytes of a ragged vector entered in state st
-HC_DEV_NOINLINE u32 rle_dec_cls_partial(u32 e, u32 vm, u32 st)
+// count-byte mask of the valid bytes of a ragged segment entered in state st
+HC_DEV_NOINLINE u64 rle_dec_cls_partial(u64 e, u64 vm, u32 st)
 {
-    u32 cm = 0;
-    for (u32 k = 0; k < 16u; k++) {
-        if (!((vm >> k) & 1u)) continue;
-        if (st == 3u) { cm |= 1u << k; st = 0; }
-        else st = (st == 0u) ? 1u : (((e >> k) & 1u) ? st + 1u : 1u);
+    u64 cm = 0;
+    for (u32 k = 0; k < 64u; k++) {
+        if (!((vm >> k) & 1ull)) continue;
+        if (st == 3u) { cm |= 1ull << k; st = 0; }
+        else st = (st == 0u) ? 1u : (((e >> k) & 1ull) ? st + 1u : 1u);
     }
     return cm;
 }
@@ -450,74 +491,49 @@ HC_DEV_NOINLINE u32 rle_dec_cls_partial(u32 e, u32 vm, u32 st)
 // spread the low 4 bits of m to the four byte lanes of a word (0xff per set bit)
 HC_DEV u32 spread4(u32 m) { return (((m & 15u) * 0x00204081u) & 0x01010101u) * 0xffu; }
 
-// sum of the bytes of v selected by the 16-bit mask cm
-HC_DEV u32 rle_masked_byte_sum(const uint4 &v, u32 cm)
+template <class Op>
+HC_DEV u64 block_scan1_u64(u64 v, u64 &excl, Op op, u64 *wtot)
 {
-    return dp4a_u(v.x & spread4(cm), 0x01010101u, 0u) + dp4a_u(v.y & spread4(cm >> 4), 0x01010101u, 0u) +
-           dp4a_u(v.z & spread4(cm >> 8), 0x01010101u, 0u) + dp4a_u(v.w & spread4(cm >> 12), 0x01010101u, 0u);
-}
-
-// generic expansion of one vector into the current output window [w0, w1): every token drops its
-// value and a head flag at its first output position inside the window
-HC_DEV_NOINLINE void rle_dec_scatter(uint4 v, u32 vm, u32 cm, u32 pb, u32 o, u32 w0, u32 w1, u8 *sval, u32 *heads)
-{
-    u32 prev = pb;
+    const u32 lane = lane_id(), w = warp_id();
+    u64 inc = v;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const u32 x = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
-        const u32 c4 = (cm >> (4 * i)) & 15u, v4 = (vm >> (4 * i)) & 15u;
-        if (c4 == 0u && v4 == 15u && o >= w0 && o + 4u <= w1) {
-            // four literals inside the window
-            const u32 pos = o - w0, sh = pos & 31u;
-            if ((pos & 3u) == 0u) *(u32 *)(sval + pos) = x;
-            else { sval[pos] = (u8)x; sval[pos + 1u] = (u8)(x >> 8); sval[pos + 2u] = (u8)(x >> 16); sval[pos + 3u] = (u8)(x >> 24); }
-            atomic_or_shared(&heads[pos >> 5], 15u << sh);
-            if (sh > 28u) atomic_or_shared(&heads[(pos >> 5) + 1u], 15u >> (32u - sh));
-            o += 4u;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const u32 b = (x >> (8 * k)) & 0xffu;
-                if ((v4 >> k) & 1u) {
-                    const bool is_cnt = (c4 >> k) & 1u;
-                    const u32 len = is_cnt ? b : 1u, val = is_cnt ? prev : b;
-                    if (len && o < w1 && o + len > w0) {
-                        const u32 pos = (o > w0 ? o : w0) - w0;
-                        sval[pos] = (u8)val;
-                        atomic_or_shared(&heads[pos >> 5], 1u << (pos & 31u));
-                    }
-                    o += len;
-                }
-                prev = b;
-            }
-        }
-        prev = x >> 24;
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 t = shfl_up64(inc, d);
+        if (lane >= (u32)d) inc = op(t, inc);
     }
-}
-
-// the common case of rle_dec_scatter: 16 literals that all lie inside the window, at window offset pos
-HC_DEV_NOINLINE void rle_dec_scatter_literals(uint4 v, u32 pos, u32 sval_addr, u32 *heads)
-{
-    stage_put16(sval_addr, pos, v);
-    const u32 sh = pos & 31u;
-    atomic_or_shared(&heads[pos >> 5], 0xffffu << sh);
-    if (sh > 16u) atomic_or_shared(&heads[(pos >> 5) + 1u], 0xffffu >> (32u - sh));
-}
-
-// fills 16 output bytes from the head flags hb / values at sval + wbase, carrying the current value
-struct Fill16 { uint4 r; u32 c; };
-HC_DEV_NOINLINE Fill16 rle_dec_fill16(u32 hb, const u8 *sv, u32 c)
-{
-    u32 wv[4] = {0, 0, 0, 0};
+    if (lane == 31) wtot[w] = inc;
+    syncthreads();
+    u64 pin = wtot[lane & 7u];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        if ((hb >> k) & 1u) c = sv[k];
-        wv[k >> 2] |= c << (8 * (k & 3));
+    for (int d = 1; d < 8; d <<= 1) {
+        const u64 t = shfl_up64(pin, d);
+        if ((lane & 7u) >= (u32)d) pin = op(t, pin);
     }
-    Fill16 f;
-    f.r.x = wv[0]; f.r.y = wv[1]; f.r.z = wv[2]; f.r.w = wv[3];
-    f.c = c;
-    return f;
+    const u64 total = shfl64(pin, 7);
+    u64 base = shfl64(pin, (int)(w ? w - 1u : 0u));
+    if (w == 0) base = 0;
+    u64 le = shfl_up64(inc, 1);
+    if (lane == 0) le = 0;
+    excl = op(base, le);
+    return total;
+}
+struct OpAdd64 { HC_DEVM u64 operator()(u64 a, u64 b) const { return a + b; } };
+
+// position of the writer in bytes from the start of the staging buffer
+HC_DEV u32 ew_pos(const EncWriter &w, u32 stage_addr) { return w.waddr - stage_addr + w.fill; }
+
+// leave the next b bytes to a run (pass B of the decoder fills them after the literals): the word under
+// assembly goes out as it is if the run reaches its end -- whatever a word store puts into bytes of the thread's
+// own runs is overwritten afterwards
+HC_DEV void ew_jump(EncWriter &w, u32 b)
+{
+    const u32 f = w.fill + b;
+    const bool shared = w.waddr == w.first;
+    if (f >= 4u && !shared) sts32(stage_swz(w.waddr), w.w0);
+    if (f >= 4u && shared) w.head = w.w0;
+    if (f >= 4u) w.w0 = 0u;
+    w.waddr += f & ~3u;
+    w.fill = f & 3u;
 }
 
 // Decodes the n0-byte token stream at src0 (any alignment) to dst (16-byte aligned, or null to
@@ -527,152 +543,187 @@ HC_DEV_NOINLINE Fill16 rle_dec_fill16(u32 hb, const u8 *sv, u32 c)
 // The kernel must have called rle_dec_init() before.
 HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT dst, u64 cap)
 {
-    HC_SHARED u32 wtot[2][32];
-    HC_SHARED u32 wlast[NW];
-    HC_SHARED u32 heads[DEC_WIN / 32 + 1];
-    HC_SHARED HC_ALIGNED16 u8 sval[DEC_WIN];
-    HC_SMEM_ARENA(wtot);
-    const RleDecTables *tb = rle_dec_tables();
-    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    RleDecShared *sh = rle_dec_shared();
+    HC_SMEM_ARENA(*sh);
+    const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 lead = n0 ? (u32)((uintptr_t)src0 & 15u) : 0u;
     const u8 *src = src0 - lead;
     const u64 n = n0 + lead;
-    const u32 sval_addr = smem_addr(sval);
+    const u32 stage = smem_addr(sh->stage);
+    const u32 base = tid * DEC_W;
     u64 out_pos = 0;
     u32 carry_state = 0;
 
-    uint4 cur[UN], nxt[UN];
-    u32 hcur[UN], hnxt[UN];          // lane 0: the byte before its vector (prefetched with the vector)
+    for (u64 t0 = 0; t0 < n; t0 += DEC_TILE) {
+        // (no register prefetch of the next tile here: the other resident CTAs cover the load latency, and the
+        // expansion below needs the registers)
+        const u64 g0 = t0 + base;
+        uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < UN; j++) {
-        u64 p = (u64)j * SUB_BYTES + tid * 16;
-        cur[j] = p < n ? ldg16(src + p) : make_uint4_zero();
-        hcur[j] = (lane == 0 && p > 0 && p < n) ? ldg8(src + p - 1) : 0u;
-    }
-    for (u64 t0 = 0; t0 < n; t0 += TILE_BYTES) {
-#pragma unroll
-        for (int j = 0; j < UN; j++) {
-            u64 p = t0 + TILE_BYTES + (u64)j * SUB_BYTES + tid * 16;
-            nxt[j] = p < n ? ldg16(src + p) : make_uint4_zero();
-            hnxt[j] = (lane == 0 && p < n) ? ldg8(src + p - 1) : 0u;
+        for (int i = 0; i < 4; i++) {
+            const u64 p = g0 + 16u * i;
+            v[i] = p < n ? ldg16_l1(src + p) : make_uint4_zero();
         }
-        // ---- scan 1: decoder state maps -----------------------------------------------
-        u32 eq[UN], valid[UN], pbyte[UN], fmap[UN], mexcl[UN];
-#pragma unroll
-        for (int j = 0; j < UN; j++) {
-            const u64 p = t0 + (u64)j * SUB_BYTES + tid * 16;
-            u32 pb = shfl_up(cur[j].w >> 24, 1);
-            if (lane == 0) pb = hcur[j];
-            pbyte[j] = pb;
-            u32 vm = p >= n ? 0u : (n - p >= 16 ? 0xffffu : ((1u << (u32)(n - p)) - 1u));
-            if (p == 0) vm &= ~((1u << lead) - 1u);
-            const u32 e = rle_eq_mask16(cur[j], pb);
-            eq[j] = e;
-            valid[j] = vm;
-            fmap[j] = vm == 0xffffu ? map_compose(tb->map8[e & 0xffu], tb->map8[(e >> 8) & 0xffu])
-                                    : (vm ? rle_dec_map_partial(e, vm) : MAP_ID);
-        }
-        u32 tile_map = block_scan_striped(fmap, mexcl, MAP_ID, OpCompose(), wtot[0]);
+        u32 hb = 0;
+        if (lane == 0 && g0 > 0 && g0 < n) hb = ldg8(src + g0 - 1);
 
-        // ---- scan 2: which bytes are counts, output length of every vector ------------
-        u32 cmask[UN], cnt[UN], oexcl[UN];
-#pragma unroll
-        for (int j = 0; j < UN; j++) {
-            const u32 s = map_apply(mexcl[j], carry_state);
-            u32 cm;
-            if (valid[j] == 0xffffu) {
-                const u32 c0 = tb->cls8[s][eq[j] & 0xffu];
-                const u32 c1 = tb->cls8[c0 >> 8][(eq[j] >> 8) & 0xffu];
-                cm = (c0 & 0xffu) | ((c1 & 0xffu) << 8);
-            } else {
-                cm = valid[j] ? rle_dec_cls_partial(eq[j], valid[j], s) : 0u;
-            }
-            cmask[j] = cm;
-            cnt[j] = (u32)popc(valid[j] & ~cm) + rle_masked_byte_sum(cur[j], cm);
+        // ---- scan 1: decoder state maps -----------------------------------------------
+        u32 pb = shfl_up(v[3].w >> 24, 1);
+        if (lane == 0) pb = hb;
+        const u64 E = (u64)rle_eq32(pb << 24, v[0], v[1]) | ((u64)rle_eq32(v[1].w, v[2], v[3]) << 32);
+        u64 V = ~0ull;
+        if (g0 + DEC_W > n || g0 == 0) {
+            const u32 cv = g0 < n ? (n - g0 >= 64u ? 64u : (u32)(n - g0)) : 0u;
+            V = cv >= 64u ? ~0ull : ((1ull << cv) - 1ull);
+            if (g0 == 0) V &= ~((1ull << lead) - 1ull);
         }
-        u32 total = block_scan_striped(cnt, oexcl, 0u, OpAdd(), wtot[1]);
+        u32 fmap;
+        if (V == ~0ull) {
+            // right to left: the table holds every 8-byte map as a PRMT selector as well
+            fmap = sh->map8[(u32)(E >> 56)];
+#pragma unroll
+            for (int i = 6; i >= 0; i--) fmap = prmt_raw(fmap, 0u, sh->sel8[(u32)(E >> (8 * i)) & 0xffu]);
+        } else {
+            fmap = V ? rle_dec_map_partial(E, V) : MAP_ID;
+        }
+        u32 mexcl;
+        const u32 tile_map = block_scan1(fmap, mexcl, MAP_ID, OpCompose(), sh->wtot[0]);
+
+        // ---- scan 2: which bytes are counts, output length and number of runs of every thread ------
+        u64 cm;
+        {
+            u32 s = map_apply(mexcl, carry_state);
+            if (V == ~0ull) {
+                cm = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const u32 c = sh->cls8[s][(u32)(E >> (8 * i)) & 0xffu];
+                    cm |= (u64)(c & 0xffu) << (8 * i);
+                    s = c >> 8;
+                }
+            } else {
+                cm = V ? rle_dec_cls_partial(E, V, s) : 0ull;
+            }
+        }
+        u32 olen = (u32)popcll(V & ~cm);
+        if (cm) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const u32 c4 = (u32)(cm >> (4 * i)) & 15u;
+                if (c4) olen = dp4a_u(vec_word(v[i >> 2], i & 3) & spread4(c4), 0x01010101u, olen);
+            }
+        }
+        const u32 nruns = (u32)popcll(cm);
+        u64 sexcl;
+        const u64 stot = block_scan1_u64((u64)olen | ((u64)nruns << 32), sexcl, OpAdd64(), sh->wtot64);
+        const u32 total = (u32)stot, oexcl = (u32)sexcl, rexcl = (u32)(sexcl >> 32);
         carry_state = map_apply(tile_map, carry_state);
 
-        // ---- expansion, one 16 KiB output window at a time ---------------------------
+        // ---- expansion, one output window at a time -----------------------------------
+        // Window w0 holds the threads whose output STARTS in [w0, w0 + DEC_WIN) with all of their output (the
+        // staging buffer has room for the longest output of one thread behind the window), so every thread
+        // is expanded exactly once and nothing is ever clipped.
         if (dst) {
             const u32 shift = (u32)(out_pos & 15u);
-            // window coordinates: w = shift + tile-relative output position
+            const u32 o = shift + oexcl;               // window coordinates: shift + tile-relative output position
+            u32 done = shift;                          // everything below has been written to dst
             for (u32 w0 = 0; w0 < shift + total; w0 += DEC_WIN) {
-                const u32 w1 = w0 + DEC_WIN;
-                for (u32 i = tid; i < DEC_WIN / 32; i += TPB) heads[i] = 0;
+                if (tid == 0) { sh->ilo = 0xffffffffu; sh->ihi = 0u; sh->wend = done; }
                 syncthreads();
+                // pass A: literals into the window, runs into the run list
+                const bool active = (olen | nruns) && o >= w0 && o < w0 + DEC_WIN;
+                u32 rlo = 0xffffffffu, rhi = 0u;
+                if (active) {
+                    if (nruns) { rlo = rexcl; rhi = rexcl + nruns; }
+                    u32 ri = rexcl;
+                    EncWriter w;
+                    ew_init(w, stage, o - w0);
 #pragma unroll
-                for (int j = 0; j < UN; j++) {
-                    const u32 o = shift + oexcl[j];
-                    if (cnt[j] == 0u || o >= w1 || o + cnt[j] <= w0) continue;
-                    if (cmask[j] == 0u && valid[j] == 0xffffu && o >= w0 && o + 16u <= w1)
-                        rle_dec_scatter_literals(cur[j], o - w0, sval_addr, heads);
-                    else
-                        rle_dec_scatter(cur[j], valid[j], cmask[j], pbyte[j], o, w0, w1, sval, heads);
-                }
-                syncthreads();
-                // each thread fills 64 consecutive output bytes of the window
-                u32 h0 = heads[2 * tid], h1 = heads[2 * tid + 1];
-                u32 mylast = h1 ? 64u * tid + 32u + (31u - (u32)clz(h1)) + 1u
-                                : (h0 ? 64u * tid + (31u - (u32)clz(h0)) + 1u : 0u);
-                // exclusive max-scan over threads: last head before this thread's range
-                u32 inc = mylast;
+                    for (int g = 0; g < 4; g++) {
+                        const u32 v16 = (u32)(V >> (16 * g)) & 0xffffu, c16 = (u32)(cm >> (16 * g)) & 0xffffu;
+                        if (v16 == 0u) continue;
+                        if (v16 == 0xffffu && c16 == 0u) { ew_put16(w, v[g]); continue; }
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    u32 t = shfl_up(inc, d);
-                    if (lane >= (u32)d && t > inc) inc = t;
-                }
-                if (lane == 31) wlast[wid] = inc;
-                syncthreads();
-                u32 before = 0;
-                for (u32 i = 0; i < wid; i++) before = wlast[i] > before ? wlast[i] : before;
-                u32 le = shfl_up(inc, 1);
-                if (lane == 0) le = 0;
-                if (le > before) before = le;
-                u32 curv = before ? sval[before - 1u] : 0u;
-                const u32 lim = (shift + total - w0) < DEC_WIN ? (shift + total - w0) : DEC_WIN;  // valid bytes in window
-                const u32 lo_valid = w0 == 0 ? shift : 0u;
-                u8 *gbase = dst + (out_pos - shift) + w0;        // 16-byte aligned
-                const u64 gpos0 = out_pos - shift + w0;          // file-relative position of window byte 0
-                const u64 capw = cap > gpos0 ? cap - gpos0 : 0;  // clip against the caller's capacity
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const u32 wbase = 64u * tid + 16u * c;
-                    const u32 hb = ((c < 2 ? h0 : h1) >> (16u * (c & 1))) & 0xffffu;
-                    uint4 r;
-                    if (hb == 0xffffu) {                          // 16 literals: the values as they are
-                        r = *(const uint4 *)(sval + wbase);
-                        curv = r.w >> 24;
-                    } else if (hb == 0u) {                        // inside a run
-                        r.x = r.y = r.z = r.w = curv * 0x01010101u;
-                    } else {
-                        const Fill16 f = rle_dec_fill16(hb, sval + wbase, curv);
-                        r = f.r;
-                        curv = f.c;
+                        for (int j = 0; j < 4; j++) {
+                            const u32 v4 = (v16 >> (4 * j)) & 15u, c4 = (c16 >> (4 * j)) & 15u;   // at most one count per word
+                            const u32 x = vec_word(v[g], j);
+                            const u32 lit = v4 & ~c4, below = c4 - 1u;                 // below: all ones without a count
+                            const u32 mb = lit & below;
+                            ew_put4(w, prmt_raw(x, 0u, sh->lut4[mb]), (u32)popc(mb));
+                            if (c4) {
+                                // the word before x (its top byte precedes byte 0 of x)
+                                const u32 pw = j ? vec_word(v[g], j ? j - 1 : 0) : (g ? v[g ? g - 1 : 0].w : pb << 24);
+                                const u32 sp = spread4(c4);
+                                const u32 b = dp4a_u(x & sp, 0x01010101u, 0u);
+                                const u32 prev = dp4a_u(funnel_l(pw, x, 8) & sp, 0x01010101u, 0u);
+                                sh->rpos[ri] = (ew_pos(w, stage) + w0) | (b << 22);
+                                sh->rval[ri] = (u8)prev;
+                                ri++;
+                                ew_jump(w, b);
+                                const u32 ma = lit & ~below;
+                                ew_put4(w, prmt_raw(x, 0u, sh->lut4[ma]), (u32)popc(ma));
+                            }
+                        }
                     }
-                    if (wbase < lim) {
-                        u32 a = wbase < lo_valid ? lo_valid : wbase;
-                        u32 b = wbase + 16u > lim ? lim : wbase + 16u;
-                        if (b > capw) b = (u32)capw;
-                        if (a == wbase && b == wbase + 16u) {
-                            stg16(gbase + wbase, r);
+                    ew_finish(w);
+                }
+                rlo = reduce_min(rlo);
+                rhi = reduce_max(rhi);
+                const u32 myend = reduce_max(active ? o + olen : 0u);
+                if (lane == 0 && myend) {
+                    atomic_max_smem(&sh->wend, myend);
+                    if (rhi) { atomic_min_smem(&sh->ilo, rlo); atomic_max_smem(&sh->ihi, rhi); }
+                }
+                syncthreads();
+                // pass B: the runs of these threads, one thread per run
+                {
+                    const u32 ilo = sh->ilo, ihi = sh->ihi;
+                    for (u32 i = ilo + tid; i < ihi; i += TPB) {
+                        const u32 e = sh->rpos[i], len = e >> 22;
+                        if (len == 0u) continue;
+                        const u32 val = sh->rval[i], val4 = val * 0x01010101u;
+                        u32 q = (e & 0x3fffffu) - w0;
+                        const u32 qe = q + len;
+                        while ((q & 3u) && q < qe) { sts8(stage_swz(stage + q), val); q++; }
+                        for (; q + 4u <= qe; q += 4u) sts32(stage_swz(stage + q), val4);
+                        for (; q < qe; q++) sts8(stage_swz(stage + q), val);
+                    }
+                }
+                syncthreads();
+                // pass C: copy [done, wend) out, clipped to the caller's capacity
+                {
+                    const u32 wbeg = done - w0;
+                    u32 wend = sh->wend - w0;
+                    done = sh->wend;
+                    u8 *gbase = dst + (out_pos - shift) + w0;        // 16-byte aligned
+                    const u64 gpos0 = out_pos - shift + w0;          // file-relative position of window byte 0
+                    const u64 capw = cap > gpos0 ? cap - gpos0 : 0;
+                    if (wend > capw) wend = (u32)capw;
+                    for (u32 c = wbeg / 16u + tid; c * 16u < wend; c += TPB) {
+                        const u32 lo = c * 16u, hi = lo + 16u;
+                        if (lo >= wbeg && hi <= wend) {
+                            const u32 sa = stage_swz(stage + lo);
+                            const uint2 a = lds64(sa), b = lds64(sa + 8u);
+                            uint4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+                            stg16(gbase + lo, r);
                         } else {
-                            for (u32 i = a; i < b; i++) gbase[i] = vec_byte(r, (int)(i - wbase));
+                            const u32 a = lo < wbeg ? wbeg : lo, b = hi > wend ? wend : hi;
+                            for (u32 i = a; i < b; i++) gbase[i] = (u8)lds8(stage_swz(stage + i));
                         }
                     }
                 }
-                syncthreads();
             }
         }
         out_pos += total;
-#pragma unroll
-        for (int j = 0; j < UN; j++) { cur[j] = nxt[j]; hcur[j] = hnxt[j]; }
         syncthreads();
     }
     return out_pos;
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(256, 3)
+#ifndef HC_RLE_DEC_MINB
+#define HC_RLE_DEC_MINB 3
+#endif
+HC_KERNEL HC_LAUNCH_BOUNDS(256, HC_RLE_DEC_MINB)
 rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
                   u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
