@@ -181,6 +181,8 @@ HC_DEV u32 smem_addr(const void *p) { return (u32)((const unsigned char *)p - g_
 HC_DEV uint2 lds64(u32 a) { uint2 v; memcpy(&v, g_emu_smem_base + a, 8); return v; }
 HC_DEV u32 lds32(u32 a) { u32 v; memcpy(&v, g_emu_smem_base + a, 4); return v; }
 HC_DEV u32 lds16(u32 a) { u16 v; memcpy(&v, g_emu_smem_base + a, 2); return v; }
+HC_DEV uint4 lds128(u32 a) { uint4 v; memcpy(&v, g_emu_smem_base + a, 16); return v; }
+HC_DEV void prefetch_l2(const void *) {}
 HC_DEV u32 lds8(u32 a) { return g_emu_smem_base[a]; }
 HC_DEV void sts64(u32 a, uint2 v) { memcpy(g_emu_smem_base + a, &v, 8); }
 HC_DEV void sts32(u32 a, u32 v) { memcpy(g_emu_smem_base + a, &v, 4); }
@@ -255,6 +257,14 @@ HC_DEV uint2 lds64(u32 a)
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
+HC_DEV uint4 lds128(u32 a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+// ask L2 for the line that holds p (no register, no dependency)
+HC_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 HC_DEV u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 HC_DEV u32 lds16(u32 a) { u32 v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 HC_DEV u32 lds8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }

@@ -362,9 +362,7 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
             for (u32 c = tid; c < nchunk; c += TPB) {
                 const u32 lo = c * 16u, hi = lo + 16u;
                 if (lo >= shift && hi <= end) {
-                    const uint2 a = lds64(stage_swz(stage + lo)), b = lds64(stage_swz(stage + lo) + 8u);
-                    uint4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
-                    stg16(gbase + lo, r);
+                    stg16(gbase + lo, lds128(stage_swz(stage + lo)));
                 } else {
                     const u32 a = lo < shift ? shift : lo, b = hi > end ? end : hi;
                     for (u32 i = a; i < b; i++) gbase[i] = (u8)lds8(stage_swz(stage + i));
@@ -430,8 +428,7 @@ struct RleDecShared {
     u32 lut4[16];
     u32 wtot[2][NW];
     u64 wtot64[NW];
-    u32 ilo, ihi;                // runs of the threads of the current window
-    u32 wend;                    // end of their output
+    u32 ctl[2][4];               // per window (alternating): first / last + 1 run of its threads, end of their output
 };
 static_assert(sizeof(RleDecShared) <= 47u * 1024u, "static shared memory");
 
@@ -566,6 +563,7 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
         }
         u32 hb = 0;
         if (lane == 0 && g0 > 0 && g0 < n) hb = ldg8(src + g0 - 1);
+        if (g0 + DEC_TILE < n) prefetch_l2(src + g0 + DEC_TILE);
 
         // ---- scan 1: decoder state maps -----------------------------------------------
         u32 pb = shfl_up(v[3].w >> 24, 1);
@@ -588,6 +586,8 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
         }
         u32 mexcl;
         const u32 tile_map = block_scan1(fmap, mexcl, MAP_ID, OpCompose(), sh->wtot[0]);
+        // (every thread has left the previous tile's last window; nobody touches ctl[0] before the next barrier)
+        if (tid == 0) { sh->ctl[0][0] = 0xffffffffu; sh->ctl[0][1] = 0u; sh->ctl[0][2] = (u32)(out_pos & 15u); }
 
         // ---- scan 2: which bytes are counts, output length and number of runs of every thread ------
         u64 cm;
@@ -627,9 +627,12 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
             const u32 shift = (u32)(out_pos & 15u);
             const u32 o = shift + oexcl;               // window coordinates: shift + tile-relative output position
             u32 done = shift;                          // everything below has been written to dst
-            for (u32 w0 = 0; w0 < shift + total; w0 += DEC_WIN) {
-                if (tid == 0) { sh->ilo = 0xffffffffu; sh->ihi = 0u; sh->wend = done; }
-                syncthreads();
+            // first position (these coordinates) that the caller's capacity does not cover
+            const u64 room = cap > out_pos - shift ? cap - (out_pos - shift) : 0;
+            const u32 climit = room < 0xfffffff0ull ? (u32)room : 0xfffffff0u;
+            u32 kp = 0;                                // the control words of this window
+            for (u32 w0 = 0; w0 < shift + total; w0 += DEC_WIN, kp ^= 1u) {
+                if (w0) syncthreads();                 // the copy-out of the previous window has read the staging buffer
                 // pass A: literals into the window, runs into the run list
                 const bool active = (olen | nruns) && o >= w0 && o < w0 + DEC_WIN;
                 u32 rlo = 0xffffffffu, rhi = 0u;
@@ -671,52 +674,50 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
                 rhi = reduce_max(rhi);
                 const u32 myend = reduce_max(active ? o + olen : 0u);
                 if (lane == 0 && myend) {
-                    atomic_max_smem(&sh->wend, myend);
-                    if (rhi) { atomic_min_smem(&sh->ilo, rlo); atomic_max_smem(&sh->ihi, rhi); }
+                    atomic_max_smem(&sh->ctl[kp][2], myend);
+                    if (rhi) { atomic_min_smem(&sh->ctl[kp][0], rlo); atomic_max_smem(&sh->ctl[kp][1], rhi); }
                 }
                 syncthreads();
+                const u32 ilo = sh->ctl[kp][0], ihi = sh->ctl[kp][1], wend_abs = sh->ctl[kp][2];
+                // the next window's control words: their last readers left them before the barrier above, their next
+                // writers come after the next one
+                if (tid == 0) { sh->ctl[kp ^ 1u][0] = 0xffffffffu; sh->ctl[kp ^ 1u][1] = 0u; sh->ctl[kp ^ 1u][2] = wend_abs; }
                 // pass B: the runs of these threads, one thread per run
-                {
-                    const u32 ilo = sh->ilo, ihi = sh->ihi;
-                    for (u32 i = ilo + tid; i < ihi; i += TPB) {
-                        const u32 e = sh->rpos[i], len = e >> 22;
-                        if (len == 0u) continue;
-                        const u32 val = sh->rval[i], val4 = val * 0x01010101u;
-                        u32 q = (e & 0x3fffffu) - w0;
-                        const u32 qe = q + len;
-                        while ((q & 3u) && q < qe) { sts8(stage_swz(stage + q), val); q++; }
-                        for (; q + 4u <= qe; q += 4u) sts32(stage_swz(stage + q), val4);
-                        for (; q < qe; q++) sts8(stage_swz(stage + q), val);
-                    }
+                for (u32 i = ilo + tid; i < ihi; i += TPB) {
+                    const u32 e = sh->rpos[i], len = e >> 22;
+                    if (len == 0u) continue;
+                    const u32 val = sh->rval[i], val4 = val * 0x01010101u;
+                    u32 q = (e & 0x3fffffu) - w0;
+                    const u32 qe = q + len;
+                    while ((q & 3u) && q < qe) { sts8(stage_swz(stage + q), val); q++; }
+                    for (; q + 4u <= qe; q += 4u) sts32(stage_swz(stage + q), val4);
+                    for (; q < qe; q++) sts8(stage_swz(stage + q), val);
                 }
                 syncthreads();
                 // pass C: copy [done, wend) out, clipped to the caller's capacity
                 {
                     const u32 wbeg = done - w0;
-                    u32 wend = sh->wend - w0;
-                    done = sh->wend;
+                    const u32 wend = (wend_abs < climit ? wend_abs : climit) - w0;     // (done <= climit or nothing is copied)
+                    done = wend_abs;
                     u8 *gbase = dst + (out_pos - shift) + w0;        // 16-byte aligned
-                    const u64 gpos0 = out_pos - shift + w0;          // file-relative position of window byte 0
-                    const u64 capw = cap > gpos0 ? cap - gpos0 : 0;
-                    if (wend > capw) wend = (u32)capw;
-                    for (u32 c = wbeg / 16u + tid; c * 16u < wend; c += TPB) {
-                        const u32 lo = c * 16u, hi = lo + 16u;
-                        if (lo >= wbeg && hi <= wend) {
-                            const u32 sa = stage_swz(stage + lo);
-                            const uint2 a = lds64(sa), b = lds64(sa + 8u);
-                            uint4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
-                            stg16(gbase + lo, r);
-                        } else {
-                            const u32 a = lo < wbeg ? wbeg : lo, b = hi > wend ? wend : hi;
-                            for (u32 i = a; i < b; i++) gbase[i] = (u8)lds8(stage_swz(stage + i));
+                    if (wend_abs != 0u && wbeg < wend && climit > w0) {
+                        for (u32 c = wbeg / 16u + tid; c * 16u < wend; c += TPB) {
+                            const u32 lo = c * 16u, hi = lo + 16u;
+                            if (lo >= wbeg && hi <= wend) {
+                                stg16(gbase + lo, lds128(stage_swz(stage + lo)));
+                            } else {
+                                const u32 a = lo < wbeg ? wbeg : lo, b = hi > wend ? wend : hi;
+                                for (u32 i = a; i < b; i++) gbase[i] = (u8)lds8(stage_swz(stage + i));
+                            }
                         }
                     }
                 }
             }
         }
+        // (no barrier here: the next tile's scans separate its expansion from this copy-out)
         out_pos += total;
-        syncthreads();
     }
+    syncthreads();
     return out_pos;
 }
 
