@@ -303,7 +303,7 @@ extern "C" int hc_rle_encode_batch(const uint8_t *in, const uint64_t *in_off, co
 {
     (void)max_len;
     if (nf == 0) return 0;
-    HC_LAUNCH(rle_encode_kernel, dim3(file_grid(nf)), dim3(TPB), 0, stream, in, in_off, in_len, out, out_off,
+    HC_LAUNCH(rle_encode_kernel, dim3(file_grid(nf)), dim3(RTPB), 0, stream, in, in_off, in_len, out, out_off,
               out_len, nf);
     HC_CHECK_LAUNCH();
     return 0;
@@ -316,7 +316,7 @@ extern "C" int hc_rle_decode_batch(const uint8_t *in, const uint64_t *in_off, co
 {
     (void)max_len;
     if (nf == 0) return 0;
-    HC_LAUNCH(rle_decode_kernel, dim3(file_grid(nf)), dim3(TPB), 0, stream, in, in_off, in_len, out, out_off,
+    HC_LAUNCH(rle_decode_kernel, dim3(file_grid(nf)), dim3(RTPB), 0, stream, in, in_off, in_len, out, out_off,
               out_cap, out_len, status, nf);
     HC_CHECK_LAUNCH();
     return 0;
@@ -376,7 +376,7 @@ static int adapt_encode_range(const uint8_t *in, const uint64_t *in_off, const u
         HC_CHECK_LAUNCH();
         u64 gb = max_len / (ADL_MINB * ADL_MINB) + 1;
         if (gb > 16) gb = 16;
-        HC_LAUNCH(adapt_emit_large_kernel, grid2(gb, nf), dim3(TPB), 0, stream, (const u8 *)ltmp, tstride, width, height, nf,
+        HC_LAUNCH(adapt_emit_large_kernel, grid2(gb, nf), dim3(RTPB), 0, stream, (const u8 *)ltmp, tstride, width, height, nf,
                   (const u32 *)boff, os, (const u64 *)cb, out, out_off, (const i32 *)status, in, in_off, (const u32 *)cost, cs);
         HC_CHECK_LAUNCH();
     }
@@ -471,7 +471,7 @@ static int adapt_decode_range(const uint8_t *in, const uint64_t *in_off, const u
     if (lbytes) {
         u64 gb = max_out_len / (ADL_MINB * ADL_MINB) + 1;
         if (gb > 16) gb = 16;
-        HC_LAUNCH(adapt_expand_large_kernel, grid2(gb, nf), dim3(TPB), 0, stream, in, in_off, in_len, (const u32 *)ws, bs,
+        HC_LAUNCH(adapt_expand_large_kernel, grid2(gb, nf), dim3(RTPB), 0, stream, in, in_off, in_len, (const u32 *)ws, bs,
                   (const i32 *)status, nf, ltmp, tstride, out, out_off);
         HC_CHECK_LAUNCH();
         u64 gx = max_out_len / (ADL_T * ADL_T) + 1;

@@ -36,8 +36,13 @@ namespace hcd {
 // ------------------------------------------------------------------------------------------
 // A thread owns ENC_W = 64 CONSECUTIVE input bytes per tile, so that the whole run logic is a handful
 // of 64-bit mask operations per thread and both block scans carry one value per thread.
+#ifndef HC_RLE_TPB
+#define HC_RLE_TPB 256
+#endif
+constexpr int RTPB = HC_RLE_TPB;               // threads of a CTA of the RLE coder (a power of two, 64..256)
+constexpr int RNW = RTPB / 32;
 constexpr u32 ENC_W = 64;
-constexpr u32 ENC_TILE = TPB * ENC_W;                                    // 16 KiB of input per CTA step
+constexpr u32 ENC_TILE = RTPB * ENC_W;                                    // 16 KiB of input per CTA step
 constexpr u32 ENC_STAGE_BYTES = (ENC_TILE + ENC_TILE / 3 + 64 + 15) & ~15u;  // worst case 4/3 + one carried count + phase
 
 // Threads write their output bytes at a stride of about 64 bytes = 16 banks, which would serialise the
@@ -50,7 +55,7 @@ HC_DEV u32 stage_swz(u32 a) { return a ^ ((a >> 2) & 0x70u); }
 struct RleEncShared {
     u8 stage[ENC_STAGE_BYTES];   // first member: 512-byte aligned like the object
     u32 lut[256];
-    u32 wtot[2][NW];
+    u32 wtot[2][RNW];
     u32 carry;
 };
 
@@ -69,17 +74,19 @@ HC_DEV RleEncShared *rle_enc_shared()
 HC_DEV void rle_enc_init()
 {
     RleEncShared *sh = rle_enc_shared();
-    const u32 idx = threadIdx.x & 255u, k4 = idx & 15u, p4 = idx >> 4;
-    u64 sel = 0x4444444444444444ull;
-    u32 o = 0;
-    for (u32 k = 0; k < 4u; k++) {
-        if ((k4 >> k) & 1u) {
-            if ((p4 >> k) & 1u) o++;                      // nibble stays 4: the count byte's place
-            sel = (sel & ~(0xfull << (4u * o))) | ((u64)k << (4u * o));
-            o++;
+    for (u32 idx = threadIdx.x; idx < 256u; idx += RTPB) {
+        const u32 k4 = idx & 15u, p4 = idx >> 4;
+        u64 sel = 0x4444444444444444ull;
+        u32 o = 0;
+        for (u32 k = 0; k < 4u; k++) {
+            if ((k4 >> k) & 1u) {
+                if ((p4 >> k) & 1u) o++;                      // nibble stays 4: the count byte's place
+                sel = (sel & ~(0xfull << (4u * o))) | ((u64)k << (4u * o));
+                o++;
+            }
         }
+        sh->lut[idx] = (u32)(sel & 0xffffu) | ((u32)((sel >> 16) & 0xffffu) << 16);
     }
-    sh->lut[idx] = (u32)(sel & 0xffffu) | ((u32)((sel >> 16) & 0xffffu) << 16);
     syncthreads();
 }
 
@@ -111,7 +118,7 @@ HC_DEV u32 rle_eq32(u32 pw, const uint4 &v0, const uint4 &v1)
 template <class Op>
 HC_DEV u32 block_scan1(u32 v, u32 &excl, u32 identity, Op op, u32 *wtot)
 {
-    static_assert(NW == 8, "the cross-warp step scans eight partials");
+    static_assert(RNW == 2 || RNW == 4 || RNW == 8, "the cross-warp step scans RNW partials inside groups of RNW lanes");
     const u32 lane = lane_id(), w = warp_id();
     u32 inc = v;
 #pragma unroll
@@ -121,13 +128,13 @@ HC_DEV u32 block_scan1(u32 v, u32 &excl, u32 identity, Op op, u32 *wtot)
     }
     if (lane == 31) wtot[w] = inc;
     syncthreads();
-    u32 pin = wtot[lane & 7u];                            // every group of eight lanes scans the eight partials
+    u32 pin = wtot[lane & (RNW - 1u)];                    // every group of RNW lanes scans the RNW partials
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
+    for (int d = 1; d < RNW; d <<= 1) {
         const u32 t = shfl_up(pin, d);
-        if ((lane & 7u) >= (u32)d) pin = op(t, pin);
+        if ((lane & (RNW - 1u)) >= (u32)d) pin = op(t, pin);
     }
-    const u32 total = shfl(pin, 7);
+    const u32 total = shfl(pin, RNW - 1);
     u32 base = shfl(pin, (int)(w ? w - 1u : 0u));
     if (w == 0) base = identity;
     u32 le = shfl_up(inc, 1);
@@ -304,7 +311,7 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
         const u64 pre = S & e1 & e2 & ~(wrap << 1);   // starts a run and the run before it has 2 <= q' < 257
         const u64 Sq = V & ~Eq;                       // places where q == 0
         const u32 cnt = (u32)popcll(keep) + (u32)popcll(pre);
-        if (tid == TPB - 1) {
+        if (tid == RTPB - 1) {
             // run length modulo 258 at the last element of a full tile
             sh->carry = Sq ? (u32)clzll(Sq) + 1u : (z + ENC_W) % 258u;
         }
@@ -359,7 +366,7 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
             u8 *gbase = dst + out_pos - shift;              // 16-byte aligned
             const u32 end = shift + total;
             const u32 nchunk = (end + 15u) / 16u;
-            for (u32 c = tid; c < nchunk; c += TPB) {
+            for (u32 c = tid; c < nchunk; c += RTPB) {
                 const u32 lo = c * 16u, hi = lo + 16u;
                 if (lo >= shift && hi <= end) {
                     stg16(gbase + lo, lds128(stage_swz(stage + lo)));
@@ -375,7 +382,10 @@ HC_DEV u64 rle_encode_stream(const u8 *HC_RESTRICT src, u64 n, u8 *HC_RESTRICT d
     return out_pos;
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(256, 3)
+#ifndef HC_RLE_ENC_MINB
+#define HC_RLE_ENC_MINB (768 / HC_RLE_TPB)
+#endif
+HC_KERNEL HC_LAUNCH_BOUNDS(RTPB, HC_RLE_ENC_MINB)
 rle_encode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, u64 *HC_RESTRICT out_len, u32 nf)
 {
@@ -407,8 +417,8 @@ HC_DEV u32 map_compose(u32 a, u32 b) { return prmt_raw(b, 0u, map_sel(a)); }
 struct OpCompose { HC_DEVM u32 operator()(u32 a, u32 b) const { return map_compose(a, b); } };
 
 constexpr u32 DEC_W = 64;                      // token bytes per thread per tile
-constexpr u32 DEC_TILE = TPB * DEC_W;          // 16 KiB of tokens per CTA step
-constexpr u32 DEC_WIN = 16384;                 // output bytes per expansion window
+constexpr u32 DEC_TILE = RTPB * DEC_W;         // 16 KiB of tokens per CTA step
+constexpr u32 DEC_WIN = RTPB * 64;             // output bytes per expansion window
 constexpr u32 DEC_MAXRUN = DEC_TILE / 4 + 8;   // a count byte needs three literals before it
 constexpr u32 DEC_MAXOUT = 16u * 255u + 48u;   // most output bytes of one thread's 64 tokens
 constexpr u32 DEC_STAGE = DEC_WIN + ((DEC_MAXOUT + 15u) & ~15u) + 80u;
@@ -426,8 +436,8 @@ struct RleDecShared {
     u16 sel8[256];
     u16 cls8[4][256];
     u32 lut4[16];
-    u32 wtot[2][NW];
-    u64 wtot64[NW];
+    u32 wtot[2][RNW];
+    u64 wtot64[RNW];
     u32 ctl[2][4];               // per window (alternating): first / last + 1 run of its threads, end of their output
 };
 static_assert(sizeof(RleDecShared) <= 47u * 1024u, "static shared memory");
@@ -442,7 +452,7 @@ HC_DEV RleDecShared *rle_dec_shared()
 HC_DEV void rle_dec_init()
 {
     RleDecShared *t = rle_dec_shared();
-    const u32 e8 = threadIdx.x & 255u;
+    for (u32 e8 = threadIdx.x; e8 < 256u; e8 += RTPB) {
     u32 m = MAP_ID;
     for (u32 k = 0; k < 8u; k++) m = map_compose(m, ((e8 >> k) & 1u) ? MAP_EQ : MAP_NE);
     t->map8[e8] = m;
@@ -460,6 +470,7 @@ HC_DEV void rle_dec_init()
         for (u32 k = 0; k < 4u; k++)
             if ((e8 >> k) & 1u) { sel = (sel & ~(0xfu << (4u * o))) | (k << (4u * o)); o++; }
         t->lut4[e8] = sel;
+    }
     }
     syncthreads();
 }
@@ -500,13 +511,13 @@ HC_DEV u64 block_scan1_u64(u64 v, u64 &excl, Op op, u64 *wtot)
     }
     if (lane == 31) wtot[w] = inc;
     syncthreads();
-    u64 pin = wtot[lane & 7u];
+    u64 pin = wtot[lane & (RNW - 1u)];
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
+    for (int d = 1; d < RNW; d <<= 1) {
         const u64 t = shfl_up64(pin, d);
-        if ((lane & 7u) >= (u32)d) pin = op(t, pin);
+        if ((lane & (RNW - 1u)) >= (u32)d) pin = op(t, pin);
     }
-    const u64 total = shfl64(pin, 7);
+    const u64 total = shfl64(pin, RNW - 1);
     u64 base = shfl64(pin, (int)(w ? w - 1u : 0u));
     if (w == 0) base = 0;
     u64 le = shfl_up64(inc, 1);
@@ -683,7 +694,7 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
                 // writers come after the next one
                 if (tid == 0) { sh->ctl[kp ^ 1u][0] = 0xffffffffu; sh->ctl[kp ^ 1u][1] = 0u; sh->ctl[kp ^ 1u][2] = wend_abs; }
                 // pass B: the runs of these threads, one thread per run
-                for (u32 i = ilo + tid; i < ihi; i += TPB) {
+                for (u32 i = ilo + tid; i < ihi; i += RTPB) {
                     const u32 e = sh->rpos[i], len = e >> 22;
                     if (len == 0u) continue;
                     const u32 val = sh->rval[i], val4 = val * 0x01010101u;
@@ -701,7 +712,7 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
                     done = wend_abs;
                     u8 *gbase = dst + (out_pos - shift) + w0;        // 16-byte aligned
                     if (wend_abs != 0u && wbeg < wend && climit > w0) {
-                        for (u32 c = wbeg / 16u + tid; c * 16u < wend; c += TPB) {
+                        for (u32 c = wbeg / 16u + tid; c * 16u < wend; c += RTPB) {
                             const u32 lo = c * 16u, hi = lo + 16u;
                             if (lo >= wbeg && hi <= wend) {
                                 stg16(gbase + lo, lds128(stage_swz(stage + lo)));
@@ -722,9 +733,9 @@ HC_DEV u64 rle_decode_stream(const u8 *HC_RESTRICT src0, u64 n0, u8 *HC_RESTRICT
 }
 
 #ifndef HC_RLE_DEC_MINB
-#define HC_RLE_DEC_MINB 3
+#define HC_RLE_DEC_MINB (768 / HC_RLE_TPB)
 #endif
-HC_KERNEL HC_LAUNCH_BOUNDS(256, HC_RLE_DEC_MINB)
+HC_KERNEL HC_LAUNCH_BOUNDS(RTPB, HC_RLE_DEC_MINB)
 rle_decode_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                   u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const u64 *HC_RESTRICT out_cap,
                   u64 *HC_RESTRICT out_len, i32 *HC_RESTRICT status, u32 nf)
