@@ -1,30 +1,40 @@
 // rle.cuh -- MNP-5 run-length encoding kernels (reference: src/transform.cpp:137-159, 241-292).
 //
-// One CTA streams one file tile by tile (16 KiB tiles, see scan.cuh) carrying a few scalars
-// between tiles, so a batch of files needs no inter-CTA communication at all and every byte is
-// read from HBM exactly once (algorithmic traffic N + M).
+// One CTA streams one file tile by tile (16 KiB tiles) carrying a few scalars between tiles, so a
+// batch of files needs no inter-CTA communication at all and every byte is read from HBM exactly
+// once (algorithmic traffic N + M).  A thread owns 64 CONSECUTIVE bytes of a tile: the run logic is a
+// handful of 64-bit mask operations per thread and every block scan carries one value per thread.
+// Equality bits: one XOR against the stream shifted by a byte, an exact zero-byte test and a DP4A that
+// gathers eight flags per instruction pair.
 //
-// ENCODE.  Per element: k = index inside its maximal run (runs are taken over elements
-// 0..n-2, the last element is always its own literal), q = k mod 258.  The element emits
-//      [q < 3] its byte, [q == 257] the byte 255, [last of run && 2 <= q < 257] the count q-2.
-// A thread owns 16-byte vectors: equality bits by byte-SIMD compares, the two emission masks by
-// bit logic on them (rle_vec_masks; k of a vector's first element comes from a block-wide max-scan
-// of run-start positions), the output position from a block-wide exclusive add-scan of the
-// per-vector byte counts.  Output assembly is per 4-byte word: a count replaces the byte of its
-// (non-literal) element, then one PRMT with a selector from a 256-entry table compacts the word.
-// Bytes are staged in shared memory with the same 16-byte phase as the global destination and
-// copied out with 128-bit stores.
+// ENCODE (causal form).  q = index of an element inside its maximal run modulo 258 (runs are taken over
+// elements 0..n-2, the last element is a run of its own).  Element k emits
+//      [the count q' - 2 of the run that ended at k-1, if k starts a run and 2 <= q' < 257]
+//      [its byte, if q < 3]   or   [255, if q == 257]
+// so a thread needs its own bytes, the byte before them and the length of the run that reaches into them
+// (block-wide max-scan of run-start positions) -- no look-ahead.  keep / pre masks by bit logic (q >= 3
+// is E & E<<1 & E<<2); the 258 wrap can only happen in the part of a segment that continues the incoming
+// run and is patched by clearing one bit.  Output position: block-wide add-scan of popc(keep) + popc(pre).
+// Output assembly: per 4-byte word one table lookup (index = keep nibble | pre nibble << 4) gives two
+// PRMT selectors that compact the word and leave a hole where a count goes; the bytes are appended by a
+// BRANCH-FREE writer (64-bit funnel, predicated STS.32 of completed words) into a staging buffer whose
+// 16-byte chunks are permuted inside every 128-byte line, because threads write at a stride of about
+// 64 bytes = 16 banks.  Count values are stored into their holes afterwards (ffs loop over the pre mask).
+// The staging buffer is copied out with aligned 128-bit stores.
 //
-// DECODE.  Whether an input byte is a literal or a count depends on the decoder state
-// c in {0,1,2,3}, whose transition only needs c and e[i] = (in[i] == in[i-1]).  Each position is
-// therefore a 4->4 map, kept one byte per state so that composing two maps is one PRMT; the map
-// of 8 positions comes from a table indexed by their equality bits, and a block-wide scan under
-// composition gives every vector its entry state.  A second table turns (state, 8 equality bits)
-// into "which of these bytes are counts"; a block-wide add-scan of the vector lengths (literals +
-// the sum of the count bytes) places the output.  Expansion is done per 16 KiB output window:
-// every token drops its value and a head flag at its first output position, then each thread
-// fills 64 consecutive output bytes from the last head value (a max-scan finds the head that
-// reaches into its range), 16 bytes at a time with shortcuts for all-literal and in-run chunks.
+// DECODE.  Whether an input byte is a literal or a count depends on the decoder state c in {0,1,2,3},
+// whose transition only needs c and e[i] = (in[i] == in[i-1]).  Each position is therefore a 4->4 map,
+// kept one byte per state so that composing two maps is one PRMT; the map of 8 positions comes from a
+// table indexed by their equality bits (stored as map and as PRMT selector, so a thread composes its
+// eight maps right to left with one PRMT each), and a block-wide scan under composition gives every
+// thread its entry state.  A second table turns (state, 8 equality bits) into "which of these bytes are
+// counts"; one 64-bit add-scan places the output (literals + sum of the count bytes) and numbers the runs.
+// Expansion per output window: window w holds the threads whose output STARTS in [w, w + 16 KiB) with
+// all of their output (a thread yields at most 4128 bytes; the staging buffer has that much room behind
+// the window), so every thread is expanded exactly once and nothing is clipped.  Pass A: literals through
+// the same branch-free writer (a count makes the writer jump; word stores may put zeros into bytes of the
+// thread's own runs), runs into a run list at their scan-assigned slot.  Pass B: one thread per run fills
+// it (after a barrier, so it overwrites whatever pass A left there).  Pass C: aligned 128-bit copy-out.
 #pragma once
 #include "runsum.cuh"
 #include "scan.cuh"
@@ -70,7 +80,7 @@ HC_DEV RleEncShared *rle_enc_shared()
 // count byte of the run that ended just before them.  Entry = two PRMT selectors (low / high output
 // word) that move the kept bytes together and leave a zero byte where a count goes (selector nibble
 // 4 = byte 0 of the second PRMT operand, which is zero).
-// called once per kernel by all TPB threads before the first rle_encode_stream
+// called once per kernel by all RTPB threads before the first rle_encode_stream
 HC_DEV void rle_enc_init()
 {
     RleEncShared *sh = rle_enc_shared();
@@ -113,7 +123,7 @@ HC_DEV u32 rle_eq32(u32 pw, const uint4 &v0, const uint4 &v1)
     return (m0 >> 7) | (m1 << 1) | (m2 << 9) | (m3 << 17);
 }
 
-// exclusive block scan of one value per thread; wtot: NW words that no other scan touches before the
+// exclusive block scan of one value per thread; wtot: RNW words that no other scan touches before the
 // next barrier after this call.  Returns the fold of the whole block.
 template <class Op>
 HC_DEV u32 block_scan1(u32 v, u32 &excl, u32 identity, Op op, u32 *wtot)
@@ -224,7 +234,7 @@ HC_DEV void ew_finish(EncWriter &w)
     if (w.skip <= 2u && w.fill > 2u) sts8(a + 2u, w.w0 >> 16);
 }
 
-// Encodes the n-byte stream at src (16-byte aligned) to dst (any alignment); called by all TPB
+// Encodes the n-byte stream at src (16-byte aligned) to dst (any alignment); called by all RTPB
 // threads of a CTA, returns the number of bytes written.  Ends with a CTA barrier.  The kernel must
 // have called rle_enc_init() before.
 //
@@ -448,7 +458,7 @@ HC_DEV RleDecShared *rle_dec_shared()
     return &sh;
 }
 
-// called once per kernel by all TPB threads before the first rle_decode_stream
+// called once per kernel by all RTPB threads before the first rle_decode_stream
 HC_DEV void rle_dec_init()
 {
     RleDecShared *t = rle_dec_shared();
@@ -545,7 +555,7 @@ HC_DEV void ew_jump(EncWriter &w, u32 b)
 }
 
 // Decodes the n0-byte token stream at src0 (any alignment) to dst (16-byte aligned, or null to
-// only measure), writing at most cap bytes; called by all TPB threads of a CTA, returns the decoded
+// only measure), writing at most cap bytes; called by all RTPB threads of a CTA, returns the decoded
 // length.  An unaligned stream is read from the 16-byte boundary below it with the leading bytes
 // masked out (they belong to the caller's buffer: a header or the previous block's tokens).
 // The kernel must have called rle_dec_init() before.
