@@ -134,6 +134,74 @@ def test_rle_decode(be, oracle):
         assert (host[int(o) + int(n):int(o) + int(c)] == 0xEE).all()
 
 
+def _rle_fuzz_stream(rng, kind, n):
+    """Byte strings that stress the 64-byte segments, 16 KiB tiles and output windows of rle.cuh."""
+    if kind == 0:
+        a = rng.integers(0, 256, n)
+    elif kind == 1:
+        a = rng.integers(0, 2, n)
+    elif kind == 2:
+        a = rng.integers(0, 3, n) // 2
+    elif kind == 3:
+        out, tot = [], 0
+        pool = [1, 1, 2, 3, 3, 4, 5, 60, 61, 62, 63, 64, 65, 66, 190, 193, 194, 195, 255, 256, 257, 258, 259, 260, 300, 514, 515, 516, 517,
+                518, 774, 1032, 1290, 5000]
+        while tot < n:
+            L = int(rng.choice(pool))
+            out.append(np.full(L, int(rng.integers(0, 3))))
+            tot += L
+        a = np.concatenate(out)[:n] if out else np.zeros(0)
+    elif kind == 4:
+        a = np.tile(np.array([5, 5, 5, 255]), n // 4 + 1)[:n]           # as tokens: every fourth byte a count of 255
+    elif kind == 5:
+        a = np.tile(np.array([7, 7, 7, int(rng.integers(0, 256))]), n // 4 + 1)[:n]
+    else:
+        a = np.repeat(rng.integers(0, 4, n // 3 + 1), rng.integers(1, 6, n // 3 + 1))[:n]
+    return np.asarray(a).astype(np.uint8)
+
+
+def test_rle_fuzz(be, oracle):
+    """Random streams of several statistics at sizes around the segment / tile / window borders: the encoder against
+    the oracle, the decoder on the same bytes read as TOKENS (any byte string is a valid MNP-5 stream) and on the
+    encoder's output, with exact and with short capacities."""
+    rng = np.random.default_rng(2024)
+    sizes = [0, 1, 2, 3, 5, 63, 64, 65, 127, 128, 129, 255, 256, 257, 258, 259, 1000, 4095, 4096, 16383, 16384, 16385, 16384 + 64,
+             16384 * 2, 16384 * 2 + 1, 40000]
+    for it in range(6 if be.name == "emu" else 20):
+        files = [_rle_fuzz_stream(rng, int(rng.integers(0, 7)), int(rng.choice(sizes + [int(rng.integers(1, 60000))]))) for _ in range(10)]
+        src = Batch(be, [f.size for f in files], files)
+        enc = Batch(be, [be.L.hc_rle_bound(f.size) for f in files], fill=0xEE)
+        rc0(be.L.hc_rle_encode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, enc.data.ptr, enc.d_off.ptr, enc.d_len.ptr,
+                                     src.nf, src.max_len, be.stream))
+        elens = enc.lens()
+        ehost = be.download(enc.data, enc.total)
+        for i, (f, g) in enumerate(zip(files, enc.files(elens))):
+            exp = oracle.rle_encode(f)
+            assert int(elens[i]) == exp.size and np.array_equal(g, exp), (it, i, f.size)
+            o, c = int(enc.offs[i]), int(enc.caps[i])
+            assert (ehost[o + exp.size:o + c] == 0xEE).all(), (it, i)
+        # decode: the raw files as token streams, and the encoder's output
+        toks = files + [oracle.rle_encode(f) for f in files[:4]]
+        exps = [oracle.rle_decode(t) for t in toks]
+        tsrc = Batch(be, [t.size for t in toks], toks)
+        caps = [e.size if rng.random() < 0.7 else max(0, e.size - int(rng.integers(300, 3000))) for e in exps]
+        dst = Batch(be, caps, fill=0xEE)
+        st = be.upload(np.zeros(tsrc.nf, np.int32))
+        rc0(be.L.hc_rle_decode_batch(tsrc.data.ptr, tsrc.d_off.ptr, tsrc.d_len.ptr, None, None, None, dst.d_len.ptr, st.ptr,
+                                     tsrc.nf, tsrc.max_len, be.stream))
+        assert [int(x) for x in dst.lens()] == [e.size for e in exps], it
+        rc0(be.L.hc_rle_decode_batch(tsrc.data.ptr, tsrc.d_off.ptr, tsrc.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                     dst.d_len.ptr, st.ptr, tsrc.nf, tsrc.max_len, be.stream))
+        lens, sts = dst.lens(), be.download(st, tsrc.nf * 4, np.int32)
+        host = be.download(dst.data, dst.total)
+        for i, e in enumerate(exps):
+            o, c = int(dst.offs[i]), int(dst.caps[i])
+            m = min(e.size, c)
+            assert int(lens[i]) == e.size and np.array_equal(host[o:o + m], e[:m]), (it, i, toks[i].size, e.size)
+            assert (e.size > c) == (int(sts[i]) == hc_b200.HC_E_CAPACITY), (it, i)
+            assert (host[o + m:o + c] == 0xEE).all(), (it, i)
+
+
 def test_rle_decode_capacity(be, oracle):
     enc = np.tile(np.array([9, 9, 9, 200], np.uint8), 50)
     exp = oracle.rle_decode(enc)
