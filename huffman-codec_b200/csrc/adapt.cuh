@@ -418,10 +418,20 @@ adapt_index_warp_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off,
     u64 blk = 0;
     // The walk advances a few dozen tokens per step (one small block) but looks at 128: the tokens are served from a
     // 2 KiB shared-memory window that is refilled with coalesced 16-byte loads when the step's range leaves it, so
-    // that a step does not wait for global memory.
-    HC_SHARED HC_ALIGNED16 u8 win[AD_WIN_BYTES];
+    // that a step does not wait for global memory.  Decoder state maps travel as indices into the 40-element monoid
+    // (rle.cuh: MapTables): one table lookup composes two maps, classifies a lane's four tokens, applies a map.
+    HC_SHARED HC_ALIGNED16 u8 win[AD_WIN_BYTES + 16];
+    HC_SHARED HC_ALIGNED16 MapTables mt;
     HC_SMEM_ARENA(win);
     const u32 wina = smem_addr(win);
+    {
+        const uint4 *g = (const uint4 *)&g_map_tables;
+        uint4 *d = (uint4 *)&mt;
+        for (u32 i = lane; i < sizeof(MapTables) / 16u; i += 32u) d[i] = g[i];
+        syncwarp();
+    }
+    const u32 t_comp = smem_addr(mt.comp), t_bytes = smem_addr(mt.bytes), t_lane4 = smem_addr(mt.lane4), t_cls4 = smem_addr(mt.cls4);
+    const u32 m_id = mt.id, m_eq = mt.eq, m_ne = mt.ne;
     u64 wlo = 0, whi = 0;                          // file positions [wlo, whi) held in the window
     // (crafted headers: block sides beyond 32 bits saturate the block size, offsets that would wrap end the loops)
     for (u64 by = 0; by < hd.h && !err; by = by + hd.b < by ? hd.h : by + hd.b) {
@@ -434,7 +444,6 @@ adapt_index_warp_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off,
             u32 state = 0, prev_last = 0;
             while (produced < req) {
                 // 128 tokens per step: 4 consecutive bytes per lane
-                const u64 idx = pos + 4u * lane;
                 if (pos < wlo || pos + 128u > whi) {
                     syncwarp();                            // every lane is done with the old window
                     wlo = pos & ~(u64)15;
@@ -451,78 +460,78 @@ adapt_index_warp_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off,
                     }
                     syncwarp();
                 }
-                u32 b[4], nv = 0;
-                const u32 wo = wina + (u32)(idx - wlo);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const bool v = idx + k < m;
-                    b[k] = v ? lds8(wo + k) : 0u;
-                    nv += v ? 1u : 0u;
-                }
-                u32 pb = shfl_up(b[3], 1);
+                const u32 wrel = (u32)(pos - wlo);                       // window offset of the step's first token
+                const u32 rel = wrel + 4u * lane;
+                const u32 x = funnel_r(lds32(wina + (rel & ~3u)), lds32(wina + (rel & ~3u) + 4u), 8u * (rel & 3u));   // byte k = token k
+                const u64 left = m - pos;
+                const u32 av = left > 128u ? 128u : (u32)left;           // valid tokens of the step
+                const i32 nvs = (i32)av - 4 * (i32)lane;
+                const u32 nv = nvs <= 0 ? 0u : (nvs >= 4 ? 4u : (u32)nvs);
+                u32 pb = shfl_up(x >> 24, 1);
                 if (lane == 0) pb = prev_last;
-                // decoder state map of the lane's (valid) bytes
-                u32 map = MAP_ID, pr = pb;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if ((u32)k < nv) map = map_compose(map, b[k] == pr ? MAP_EQ : MAP_NE);
-                    pr = b[k];
+                // equality bits of the lane's tokens, their state map, the maps of all tokens up to the lane
+                const u32 e4 = dp4a_u(rle_zero_bytes(x ^ ((x << 8) | pb)), 0x08040201u, 0u) >> 7;
+                u32 mi;
+                if (nv == 4u) {
+                    mi = lds8(t_lane4 + e4);
+                } else {
+                    mi = m_id;
+                    for (u32 k = 0; k < nv; k++) mi = lds8(t_comp + 64u * mi + (((e4 >> k) & 1u) ? m_eq : m_ne));
                 }
-                u32 inc = map;
+                u32 inc = mi;
+#pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    u32 t = shfl_up(inc, d);
-                    if (lane >= (u32)d) inc = map_compose(t, inc);
+                    const u32 t = shfl_up(inc, d);
+                    const u32 c = lds8(t_comp + 64u * (lane >= (u32)d ? t : m_id) + inc);
+                    inc = c;
                 }
                 u32 exm = shfl_up(inc, 1);
-                if (lane == 0) exm = MAP_ID;
-                // output length of each of the lane's tokens
-                u32 s = map_apply(exm, state), len[4], sum = 0;
-                pr = pb;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    len[k] = 0;
-                    if ((u32)k < nv) {
-                        if (s == 3u) { len[k] = b[k]; s = 0; }
-                        else { len[k] = 1; s = (s == 0u) ? 1u : (b[k] == pr ? s + 1u : 1u); }
+                if (lane == 0) exm = m_id;
+                // which tokens are counts, output length of every token (one byte each: a count is at most 255)
+                const u32 s = (lds32(t_bytes + 4u * exm) >> (8u * state)) & 3u;
+                u32 cm4;
+                if (nv == 4u) {
+                    cm4 = lds8(t_cls4 + 16u * s + e4) & 15u;
+                } else {
+                    cm4 = 0;
+                    u32 st = s;
+                    for (u32 k = 0; k < nv; k++) {
+                        if (st == 3u) { cm4 |= 1u << k; st = 0; }
+                        else st = (st == 0u) ? 1u : (((e4 >> k) & 1u) ? st + 1u : 1u);
                     }
-                    pr = b[k];
-                    sum += len[k];
                 }
+                const u32 lens = (x & spread4(cm4)) | (0x01010101u & spread4(((1u << nv) - 1u) & ~cm4));
+                const u32 sum = dp4a_u(lens, 0x01010101u, 0u);
                 u32 cum = sum;
+#pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    u32 t = shfl_up(cum, d);
+                    const u32 t = shfl_up(cum, d);
                     if (lane >= (u32)d) cum += t;
                 }
                 const u64 rem = req - produced;
-                const u32 hit = ballot(nv != 0u && (u64)cum >= rem);
+                const u32 rem32 = rem > 0xffffffffull ? 0xffffffffu : (u32)rem;   // (a step yields less than 2^15 bytes)
+                const u32 hit = ballot(nv != 0u && cum >= rem32);
                 if (hit == 0u) {
                     // the step did not complete the block: consume every valid token
-                    u32 tv = nv;
-                    for (int d = 16; d > 0; d >>= 1) tv += shfl_xor(tv, d);
-                    if (tv == 0u) { err = 14; break; }                  // src/transform.cpp:170-174
+                    if (av == 0u) { err = 14; break; }                  // src/transform.cpp:170-174
                     produced += shfl(cum, 31);
-                    state = map_apply(shfl(inc, 31), state);
-                    const u32 last_lane = (tv - 1u) >> 2;
-                    {
-                        // byte value of the last consumed token (lane last_lane, slot (tv-1)&3)
-                        const u32 slot = (tv - 1u) & 3u;
-                        const u32 mine = slot == 0 ? b[0] : slot == 1 ? b[1] : slot == 2 ? b[2] : b[3];
-                        prev_last = shfl(mine, (int)last_lane);
-                    }
-                    pos += tv;
-                    if (tv < 128u && produced < req) { err = 14; break; }
+                    state = (lds32(t_bytes + 4u * shfl(inc, 31)) >> (8u * state)) & 3u;
+                    prev_last = lds8(wina + wrel + av - 1u);            // the last consumed token
+                    pos += av;
+                    if (av < 128u && produced < req) { err = 14; break; }
                 } else {
                     // the block ends inside lane `hl`: find the token
                     const int hl = ffs(hit) - 1;
                     const u32 before = shfl(cum - sum, hl);               // produced by the lanes before hl
-                    const u32 l0 = shfl(len[0], hl), l1 = shfl(len[1], hl), l2 = shfl(len[2], hl), l3 = shfl(len[3], hl);
-                    const u64 need = rem - before;                        // still missing when lane hl starts (>= 1)
+                    const u32 lh = shfl(lens, hl);
+                    const u32 l0 = lh & 0xffu, l1 = (lh >> 8) & 0xffu, l2 = (lh >> 16) & 0xffu, l3 = lh >> 24;
+                    const u32 need = rem32 - before;                      // still missing when lane hl starts (>= 1)
                     u32 tok, got;
-                    if ((u64)l0 >= need) { tok = 0; got = l0; }
-                    else if ((u64)l0 + l1 >= need) { tok = 1; got = l0 + l1; }
-                    else if ((u64)l0 + l1 + l2 >= need) { tok = 2; got = l0 + l1 + l2; }
+                    if (l0 >= need) { tok = 0; got = l0; }
+                    else if (l0 + l1 >= need) { tok = 1; got = l0 + l1; }
+                    else if (l0 + l1 + l2 >= need) { tok = 2; got = l0 + l1 + l2; }
                     else { tok = 3; got = l0 + l1 + l2 + l3; }
-                    if ((u64)got > need) { err = 13; break; }            // src/transform.cpp:180-184
+                    if (got > need) { err = 13; break; }                 // src/transform.cpp:180-184
                     pos += 4u * (u32)hl + tok + 1u;
                     produced = req;
                 }

@@ -26,6 +26,7 @@
 #define HC_RESTRICT
 #define HC_ALIGNED16 __attribute__((aligned(16)))
 #define HC_ALIGNED(n) __attribute__((aligned(n)))
+#define HC_DEVICE_CONST static constexpr
 #else
 #include <cuda_runtime.h>
 #define HC_KERNEL __global__ void
@@ -44,6 +45,7 @@
 #define HC_RESTRICT __restrict__
 #define HC_ALIGNED16 __align__(16)
 #define HC_ALIGNED(n) __align__(n)
+#define HC_DEVICE_CONST __device__ constexpr
 #endif
 
 void hc_count_launch();

@@ -426,6 +426,70 @@ HC_DEV u32 map_sel(u32 a)
 HC_DEV u32 map_compose(u32 a, u32 b) { return prmt_raw(b, 0u, map_sel(a)); }
 struct OpCompose { HC_DEVM u32 operator()(u32 a, u32 b) const { return map_compose(a, b); } };
 
+// The maps that token strings can produce form a monoid of only 40 elements (closure of {EQ, NE} under composition),
+// so a map can also travel as an index and be composed by one table lookup: the walk of the adaptive block index
+// (adapt.cuh), whose warp scans maps once per block, uses that form.  Built at compile time.
+constexpr u32 MAPT_N = 40;
+struct HC_ALIGNED16 MapTables {
+    u32 bytes[64];           // index -> the map, one byte per state
+    u8 comp[MAPT_N * 64];    // comp[a * 64 + b] = index of "first a, then b"
+    u8 lane4[16];            // four equality bits -> index of the map of four tokens
+    u8 cls4[64];             // state * 16 + four equality bits -> which of the four tokens are counts | state after << 4
+    u8 id, eq, ne, n;
+    u8 pad[12];
+};
+static_assert(sizeof(MapTables) % 16 == 0, "copied to shared memory in 16-byte pieces");
+
+constexpr u32 mapt_compose(u32 a, u32 b)      // byte forms, first a then b
+{
+    u32 r = 0;
+    for (u32 s = 0; s < 4; s++) r |= ((b >> (8 * ((a >> (8 * s)) & 3u))) & 3u) << (8 * s);
+    return r;
+}
+
+constexpr MapTables make_map_tables()
+{
+    MapTables t{};
+    u32 n = 0;
+    t.bytes[n++] = MAP_ID;
+    for (u32 i = 0; i < n; i++) {                       // breadth first: append EQ / NE to every known map
+        for (u32 g = 0; g < 2; g++) {
+            const u32 c = mapt_compose(t.bytes[i], g ? MAP_NE : MAP_EQ);
+            bool known = false;
+            for (u32 j = 0; j < n; j++) known = known || t.bytes[j] == c;
+            if (!known && n < 64) t.bytes[n++] = c;
+        }
+    }
+    t.n = (u8)n;
+    for (u32 a = 0; a < n && a < MAPT_N; a++)
+        for (u32 b = 0; b < n; b++) {
+            const u32 c = mapt_compose(t.bytes[a], t.bytes[b]);
+            for (u32 j = 0; j < n; j++) if (t.bytes[j] == c) t.comp[a * 64 + b] = (u8)j;
+        }
+    for (u32 j = 0; j < n; j++) {
+        if (t.bytes[j] == MAP_ID) t.id = (u8)j;
+        if (t.bytes[j] == MAP_EQ) t.eq = (u8)j;
+        if (t.bytes[j] == MAP_NE) t.ne = (u8)j;
+    }
+    for (u32 e4 = 0; e4 < 16; e4++) {
+        u32 m = MAP_ID;
+        for (u32 k = 0; k < 4; k++) m = mapt_compose(m, ((e4 >> k) & 1u) ? MAP_EQ : MAP_NE);
+        for (u32 j = 0; j < n; j++) if (t.bytes[j] == m) t.lane4[e4] = (u8)j;
+        for (u32 s0 = 0; s0 < 4; s0++) {
+            u32 st = s0, cm = 0;
+            for (u32 k = 0; k < 4; k++) {
+                if (st == 3u) { cm |= 1u << k; st = 0; }
+                else st = (st == 0u) ? 1u : (((e4 >> k) & 1u) ? st + 1u : 1u);
+            }
+            t.cls4[s0 * 16 + e4] = (u8)(cm | (st << 4));
+        }
+    }
+    return t;
+}
+
+HC_DEVICE_CONST MapTables g_map_tables = make_map_tables();
+static_assert(make_map_tables().n == MAPT_N, "the monoid of decoder state maps has 40 elements");
+
 constexpr u32 DEC_W = 64;                      // token bytes per thread per tile
 constexpr u32 DEC_TILE = RTPB * DEC_W;         // 16 KiB of tokens per CTA step
 constexpr u32 DEC_WIN = RTPB * 64;             // output bytes per expansion window
