@@ -123,7 +123,7 @@ adapt_gather_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_of
     }
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(RTPB, 512 / RTPB)
+HC_KERNEL HC_LAUNCH_BOUNDS(RTPB, HC_RLE_ENC_MINB)
 adapt_emit_large_kernel(const u8 *HC_RESTRICT tmp, u64 tstride, const u64 *HC_RESTRICT width, const u64 *HC_RESTRICT height,
                         u32 nf, const u32 *HC_RESTRICT blk_off, u64 off_stride, const u64 *HC_RESTRICT chosen_b,
                         u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off, const i32 *HC_RESTRICT status,
@@ -151,7 +151,7 @@ adapt_emit_large_kernel(const u8 *HC_RESTRICT tmp, u64 tstride, const u64 *HC_RE
     }
 }
 
-HC_KERNEL HC_LAUNCH_BOUNDS(RTPB, 512 / RTPB)
+HC_KERNEL HC_LAUNCH_BOUNDS(RTPB, HC_RLE_DEC_MINB)
 adapt_expand_large_kernel(const u8 *HC_RESTRICT in, const u64 *HC_RESTRICT in_off, const u64 *HC_RESTRICT in_len,
                           const u32 *HC_RESTRICT blk_start, u64 blk_stride, const i32 *HC_RESTRICT status, u32 nf,
                           u8 *HC_RESTRICT tmp, u64 tstride, u8 *HC_RESTRICT out, const u64 *HC_RESTRICT out_off)
