@@ -524,7 +524,7 @@ def run_ours(args):
             # step s: compress, then decompress of its output.  Tickets alternate compress / decompress so that the two
             # kinds land on different pipeline slots; up to depth/2 steps are in flight, a host buffer set is reused only
             # after the decompress that read it has finished.
-            ahead = depth // 2
+            ahead = max(1, min(args.ahead or depth // 2, depth // 2))
             tc, td = {}, {}
             nxt = 0                                           # next step whose compress is to be submitted
             for s in range(k_steps):
@@ -689,6 +689,7 @@ def main():
     ap.add_argument("--total-files", type=int, default=None, help="strong scaling: this many files in total, cut over the ranks")
     ap.add_argument("--overlap", type=int, default=8, help="codec streams that consecutive steps alternate between (1 = strictly one step at a time, max 8)")
     ap.add_argument("--depth", type=int, default=4, help="slots of the asynchronous host pipeline used by the e2e measurement (even: compress and decompress jobs alternate)")
+    ap.add_argument("--ahead", type=int, default=0, help="steps in flight in the e2e measurement (default and maximum: depth / 2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the -m sub-run and the saturated run")
