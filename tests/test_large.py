@@ -69,3 +69,32 @@ def test_random_image_4096(oracle):
     assert rc == 0 and outs[0].size == exp.size and np.array_equal(outs[0], exp)
     back, st = cd.decompress(outs)
     assert st[0] == 0 and np.array_equal(back[0], img)
+
+
+def test_rle_stage_multi_mib(oracle):
+    """Plain MNP-5 (`-m` without `-a`) at the file sizes of BASELINE config 4: one CTA streams hundreds of 16 KiB tiles;
+    the decoder of the flat images needs 64 output windows per token tile."""
+    be = CudaBackend()
+    rng = np.random.default_rng(5)
+    n = 4 << 20
+    flat = np.full(n, 9, np.uint8)
+    flat[rng.integers(0, n, 40)] = 200                                # a few breaks inside runs of many times 258
+    files = [oracle.diff_apply(synth.image(k, 2048, 70 + i).reshape(-1)) for i, k in enumerate(("walk", "smooth", "random", "longrun"))]
+    files += [flat, np.repeat(rng.integers(0, 4, n // 3, dtype=np.uint8), 3)[: n - 5]]
+    src = Batch(be, [f.size for f in files], files)
+    enc = Batch(be, [be.L.hc_rle_bound(f.size) for f in files], fill=0xEE)
+    assert be.L.hc_rle_encode_batch(src.data.ptr, src.d_off.ptr, src.d_len.ptr, enc.data.ptr, enc.d_off.ptr, enc.d_len.ptr,
+                                    src.nf, src.max_len, be.stream) == 0
+    elens = enc.lens()
+    outs = enc.files(elens)
+    for i, (f, g) in enumerate(zip(files, outs)):
+        exp = oracle.rle_encode(f)
+        assert int(elens[i]) == exp.size and np.array_equal(g, exp), i
+    tsrc = Batch(be, [o.size for o in outs], outs)
+    dst = Batch(be, [f.size for f in files], fill=0xEE)
+    st = be.upload(np.zeros(src.nf, np.int32))
+    assert be.L.hc_rle_decode_batch(tsrc.data.ptr, tsrc.d_off.ptr, tsrc.d_len.ptr, dst.data.ptr, dst.d_off.ptr, dst.d_cap.ptr,
+                                    dst.d_len.ptr, st.ptr, src.nf, tsrc.max_len, be.stream) == 0
+    assert not be.download(st, src.nf * 4, np.int32).any()
+    for i, (f, g) in enumerate(zip(files, dst.files(dst.lens()))):
+        assert np.array_equal(g, f), i
