@@ -395,6 +395,14 @@ HC_DEV bool fgk_update_ties(FgkCtx &c, u32 A, u32 pf, u32 lane, FgkPre pre)
         const u32 depth = pf >> 12;
         const u32 W = pre.n.x;
         const bool tie = lane < depth && pre.n1.x == W;
+        if (guard > 1u && !any(tie)) {
+            // a later round (the walk moved to another branch) without a tie -- the usual case: plain increments,
+            // without describing swaps that nobody does
+            syncwarp();                                   // this round's loads precede its stores
+            sts32_if(lane < depth, c.rec + A, W + 1u);
+            syncwarp();
+            return changed;
+        }
         const bool lng = pre.w2 == W;
         const u32 info = tie ? (lanebits | (lng ? (FGK_I_LONG | A) : fgk_swap_info(pre.n.y, pre.n1.y, A + 8u, pre.pfl))) : 0u;
         u32 hi = depth;                                   // lanes [0, hi) still have to add 1 to their node
